@@ -1,0 +1,264 @@
+"""ctypes binding of the C-ABI in ``include/b3gs.h`` — the ``_C`` module of the operator surface.
+
+The reference binds its rasterizer with pybind11
+(``submodules/diff-gaussian-rasterization/ext.cpp:15-18``) and does the tensor
+allocation in C++ (``rasterize_points.cu:35-229``).  Here the shared library has no
+torch types in its signatures, so this file is the host side above the C-ABI: it
+allocates outputs and the three opaque state blobs as torch tensors (the blobs through
+the resize callback, like ``resizeFunctional`` at ``rasterize_points.cu:27-33``),
+unwraps ``data_ptr()``/current stream, and exposes the three functions with the exact
+names, argument order and return tuples of the reference's ``_C`` module:
+
+    rasterize_gaussians(...)           -> (int, color, depth, alpha, radii, geom, binning, img)
+    rasterize_gaussians_backward(...)  -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D,
+                                           dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+    mark_visible(means3D, viewmatrix, projmatrix) -> bool tensor
+
+The class is parameterised by symbol prefix so that the test infrastructure
+(``oracle/refbackend.py``) can bind the reference's own kernels — compiled behind an
+identical C-ABI — and drive them through identical host code.  Nothing in this
+package loads anything from ``oracle/``.
+
+There is deliberately NO fallback: if the CUDA library cannot be loaded the import
+fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_RESIZE_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+class _Buffer(ctypes.Structure):
+    _fields_ = [("resize", _RESIZE_FN), ("user", ctypes.c_void_p)]
+
+
+_F = ctypes.c_void_p  # every device pointer travels as void*
+_FWD_ARGTYPES = (
+    [_Buffer, _Buffer, _Buffer, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int]
+    + [_F, _F, _F, _F, _F, ctypes.c_float, _F, _F, _F, _F, _F, ctypes.c_float, ctypes.c_float, ctypes.c_int]
+    + [_F, _F, _F, _F, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+)
+_BWD_ARGTYPES = (
+    [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F, ctypes.c_int, ctypes.c_int]
+    + [_F, _F, _F, _F, _F, ctypes.c_float, _F, _F, _F, _F, _F, ctypes.c_float, ctypes.c_float, _F]
+    + [_F, _F, _F, _F, _F, _F]
+    + [_F] * 10
+    + [ctypes.c_int, ctypes.c_void_p]
+)
+
+
+def _ptr(t: torch.Tensor):
+    """Reference null convention (rasterize_points.cu:96-115): empty tensor -> nullptr."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t is None:
+        return torch.empty(0)
+    if t.numel() == 0:
+        return t
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class Backend:
+    """One loaded rasterizer library (ours or the reference veneer)."""
+
+    def __init__(self, path: str, prefix: str, needs_zeroed_outputs: bool, name: str):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{name}: CUDA library not found at {path}. Build it with "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` — there is no CPU fallback."
+            )
+        self.path = path
+        self.name = name
+        self.prefix = prefix
+        self.needs_zeroed_outputs = needs_zeroed_outputs
+        self.lib = ctypes.CDLL(path)
+        g = lambda s: getattr(self.lib, prefix + s)
+        self._forward = g("forward")
+        self._forward.argtypes = _FWD_ARGTYPES
+        self._forward.restype = ctypes.c_int
+        self._backward = g("backward")
+        self._backward.argtypes = _BWD_ARGTYPES
+        self._backward.restype = ctypes.c_int
+        self._mark_visible = g("mark_visible")
+        self._mark_visible.argtypes = [ctypes.c_int, _F, _F, _F, _F, ctypes.c_void_p]
+        self._mark_visible.restype = ctypes.c_int
+        self._last_error = g("last_error")
+        self._last_error.restype = ctypes.c_char_p
+        self._version = g("version")
+        self._version.restype = ctypes.c_char_p
+        self._launch_count = g("launch_count")
+        self._launch_count.restype = ctypes.c_ulonglong
+        for kind in ("geometry", "binning", "image"):
+            f = g(kind + "_offset")
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p] if kind == "image" else [ctypes.c_int, ctypes.c_char_p]
+            setattr(self, "_" + kind + "_offset", f)
+            f = g(kind + "_bytes")
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.c_int, ctypes.c_int] if kind == "image" else [ctypes.c_int]
+            setattr(self, "_" + kind + "_bytes", f)
+        # One persistent C callback; `user` is the slot index (0 geom, 1 binning, 2 image).
+        self._tls = threading.local()
+        self._cb = _RESIZE_FN(self._resize)
+
+    # ------------------------------------------------------------------ helpers
+    def version(self) -> str:
+        return self._version().decode()
+
+    def launch_count(self) -> int:
+        return int(self._launch_count())
+
+    def _err(self, what: str, code: int) -> RuntimeError:
+        return RuntimeError(f"{self.name}.{what} failed ({code}): {self._last_error().decode()}")
+
+    def _resize(self, user, nbytes):
+        slot = int(user or 0)
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=self._tls.device)
+        self._tls.slots[slot] = t
+        return t.data_ptr()
+
+    def _buffers(self):
+        return (_Buffer(self._cb, 0), _Buffer(self._cb, 1), _Buffer(self._cb, 2))
+
+    def blob_view(self, blob: torch.Tensor, kind: str, name: str, dtype: torch.dtype, count: int, *dims):
+        """Slice a named internal array out of an opaque blob (parity tests only)."""
+        if kind == "image":
+            off = self._image_offset(dims[0], dims[1], name.encode())
+        else:
+            off = getattr(self, "_" + kind + "_offset")(dims[0], name.encode())
+        if off == ctypes.c_size_t(-1).value:
+            raise KeyError(name)
+        base = blob.data_ptr()
+        aligned = (base + 255) // 256 * 256 if self.prefix == "b3gs_" else (base + 127) // 128 * 128
+        off += aligned - base
+        nbytes = count * torch.empty(0, dtype=dtype).element_size()
+        return blob[off : off + nbytes].view(dtype)
+
+    # ------------------------------------------------------------------ _C surface
+    def rasterize_gaussians(
+        self, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+        prefiltered, debug,
+    ):
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+        dev = means3D.device
+        if dev.type != "cuda":
+            raise RuntimeError("means3D must be a CUDA tensor (no CPU path exists)")
+        alloc = torch.zeros if self.needs_zeroed_outputs else torch.empty
+        with torch.cuda.device(dev):
+            out_color = alloc((3, H, W), dtype=torch.float32, device=dev)
+            out_depth = alloc((1, H, W), dtype=torch.float32, device=dev)
+            out_alpha = alloc((1, H, W), dtype=torch.float32, device=dev)
+            radii = alloc((P,), dtype=torch.int32, device=dev)
+            self._tls.device = dev
+            self._tls.slots = [torch.empty(0, dtype=torch.uint8, device=dev) for _ in range(3)]
+            M = int(sh.size(1)) if sh.dim() >= 2 and sh.size(0) != 0 else 0
+            bg, m3, col, opa, sca, rot, cov, vm, pm, shs, cam = (
+                _prep(background, "background"), _prep(means3D, "means3D"), _prep(colors, "colors_precomp"),
+                _prep(opacity, "opacities"), _prep(scales, "scales"), _prep(rotations, "rotations"),
+                _prep(cov3D_precomp, "cov3D_precomp"), _prep(viewmatrix, "viewmatrix"),
+                _prep(projmatrix, "projmatrix"), _prep(sh, "sh"), _prep(campos, "campos"),
+            )
+            rendered = ctypes.c_int(0)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            g, b, i = self._buffers()
+            rc = self._forward(
+                g, b, i, P, int(degree), M, _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(opa), _ptr(sca),
+                float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
+                float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(), out_depth.data_ptr(),
+                out_alpha.data_ptr(), _ptr(radii), int(bool(debug)), stream, ctypes.byref(rendered),
+            )
+            if rc != 0:
+                raise self._err("rasterize_gaussians", rc)
+            geom, binning, img = self._tls.slots
+            self._tls.slots = None
+        return rendered.value, out_color, out_depth, out_alpha, radii, geom, binning, img
+
+    def rasterize_gaussians_backward(
+        self, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+        projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, dL_dout_alpha, sh, degree, campos,
+        geomBuffer, R, binningBuffer, imageBuffer, alphas, debug,
+    ):
+        P = int(means3D.size(0))
+        H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+        dev = means3D.device
+        M = int(sh.size(1)) if sh.dim() >= 2 and sh.size(0) != 0 else 0
+        # The reference zero-fills all ten (rasterize_points.cu:158-167); our library
+        # writes every element itself.
+        alloc = torch.zeros if (self.needs_zeroed_outputs or P == 0) else torch.empty
+        with torch.cuda.device(dev):
+            o = dict(dtype=torch.float32, device=dev)
+            dL_dmeans3D = alloc((P, 3), **o)
+            dL_dmeans2D = alloc((P, 3), **o)
+            dL_dcolors = alloc((P, 3), **o)
+            dL_ddepths = alloc((P, 1), **o)
+            dL_dconic = alloc((P, 2, 2), **o)
+            dL_dopacity = alloc((P, 1), **o)
+            dL_dcov3D = alloc((P, 6), **o)
+            dL_dsh = alloc((P, M, 3), **o)
+            dL_dscales = alloc((P, 3), **o)
+            dL_drotations = alloc((P, 4), **o)
+            if P != 0:
+                bg, m3, col, sca, rot, cov, vm, pm, shs, cam, alp, gc, gd, ga = (
+                    _prep(background, "background"), _prep(means3D, "means3D"), _prep(colors, "colors_precomp"),
+                    _prep(scales, "scales"), _prep(rotations, "rotations"), _prep(cov3D_precomp, "cov3D_precomp"),
+                    _prep(viewmatrix, "viewmatrix"), _prep(projmatrix, "projmatrix"), _prep(sh, "sh"),
+                    _prep(campos, "campos"), _prep(alphas, "alphas"), _prep(dL_dout_color, "dL_dout_color"),
+                    _prep(dL_dout_depth, "dL_dout_depth"), _prep(dL_dout_alpha, "dL_dout_alpha"),
+                )
+                rad = radii.contiguous()
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = self._backward(
+                    P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(alp), _ptr(sca),
+                    float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
+                    float(tan_fovy), _ptr(rad), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                    _ptr(gc), _ptr(gd), _ptr(ga), dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(),
+                    dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_ddepths.data_ptr(), dL_dmeans3D.data_ptr(),
+                    dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
+                    int(bool(debug)), stream,
+                )
+                if rc != 0:
+                    raise self._err("rasterize_gaussians_backward", rc)
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+    def mark_visible(self, means3D, viewmatrix, projmatrix):
+        P = int(means3D.size(0))
+        dev = means3D.device
+        present = torch.zeros((P,), dtype=torch.bool, device=dev)
+        if P != 0:
+            with torch.cuda.device(dev):
+                m3, vm, pm = _prep(means3D, "means3D"), _prep(viewmatrix, "viewmatrix"), _prep(projmatrix, "projmatrix")
+                rc = self._mark_visible(P, _ptr(m3), _ptr(vm), _ptr(pm), present.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream)
+                if rc != 0:
+                    raise self._err("mark_visible", rc)
+        return present
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb3gs.so")
+
+_native = None
+
+
+def native() -> Backend:
+    """Our sm_100a library.  Raises ImportError if it has not been built."""
+    global _native
+    if _native is None:
+        _native = Backend(LIB_PATH, "b3gs_", needs_zeroed_outputs=False, name="b3gs")
+    return _native

@@ -1,0 +1,329 @@
+// api.cu — the C-ABI (include/b3gs.h) and the forward/backward orchestration.
+//
+// Reference behaviour: rasterizer_impl.cu:197-339 (Rasterizer::forward),
+// :343-447 (::backward), :141-153 (::markVisible), rasterizer_impl.h:22-73 (state
+// blobs and the obtain/required chunk allocator).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/b3gs.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b3 {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static thread_local std::string g_error;
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_error = what;
+    if (e != cudaSuccess) {
+        g_error += ": ";
+        g_error += cudaGetErrorString(e);
+    }
+    return code;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- blob layouts: pure functions of (P), (R), (W,H) --------------------------
+struct GeomLayout {
+    size_t records, depths, tiles_touched, point_offsets, clamped, grads, scan_scratch, total;
+    explicit GeomLayout(int P) {
+        const size_t p = (size_t)(P > 0 ? P : 0);
+        size_t o = 0;
+        records = o;       o = align_up(o + p * 48, 256);
+        depths = o;        o = align_up(o + p * 4, 256);
+        tiles_touched = o; o = align_up(o + p * 4, 256);
+        point_offsets = o; o = align_up(o + p * 4, 256);
+        clamped = o;       o = align_up(o + p, 256);
+        grads = o;         o = align_up(o + p * B3_GRAD_STRIDE * 4, 256);
+        scan_scratch = o;  o = align_up(o + scan_scratch_elems(P) * 4, 256);
+        total = o + 256;
+    }
+};
+struct ImageLayout {
+    size_t n_contrib, ranges, total;
+    ImageLayout(int W, int H) {
+        const size_t n = (size_t)W * H;
+        const size_t t = (size_t)((W + B3_TILE_X - 1) / B3_TILE_X) * ((H + B3_TILE_Y - 1) / B3_TILE_Y);
+        size_t o = 0;
+        n_contrib = o; o = align_up(o + n * 4, 256);
+        ranges = o;    o = align_up(o + t * 8, 256);
+        total = o + 256;
+    }
+};
+struct BinLayout {
+    size_t point_list, scratch, scratch_bytes, total;
+    explicit BinLayout(int R, bool with_scratch = true) {
+        const size_t r = (size_t)(R > 0 ? R : 0);
+        size_t o = 0;
+        point_list = o; o = align_up(o + r * 4, 256);
+        scratch = o;
+        scratch_bytes = with_scratch ? binning_scratch_bytes(R) : 0;
+        o = align_up(o + scratch_bytes, 256);
+        total = o + 256;
+    }
+};
+
+static char* align_ptr(void* p) {
+    return reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
+}
+
+// One pinned word per host thread for the R read-back.
+static int* pinned_word() {
+    static thread_local int* w = nullptr;
+    if (!w) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&w), sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) w = nullptr;
+    }
+    return w;
+}
+
+#define B3_CHECK_STAGE(what)                                             \
+    do {                                                                 \
+        cudaError_t e_ = cudaGetLastError();                             \
+        if (e_ == cudaSuccess && debug) e_ = cudaStreamSynchronize(st);  \
+        if (e_ != cudaSuccess) return fail(B3GS_ERR_CUDA, what, e_);     \
+    } while (0)
+
+}  // namespace b3
+
+using namespace b3;
+
+extern "C" {
+
+int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
+                 const float* background, int width, int height, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                 float* out_color, float* out_depth, float* out_alpha, int* radii, int debug, void* stream,
+                 int* num_rendered) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (num_rendered) *num_rendered = 0;
+    if (P < 0 || width <= 0 || height <= 0 || D < 0 || D > 3)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: bad sizes (P>=0, width,height>0, 0<=D<=3)");
+    if (!geometry.resize || !binning.resize || !image.resize)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: null resize callback");
+    if (!out_color || !out_depth || !out_alpha || !background)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: null output/background pointer");
+    const int grid_x = (width + B3_TILE_X - 1) / B3_TILE_X, grid_y = (height + B3_TILE_Y - 1) / B3_TILE_Y;
+
+    if (P == 0) {
+        // rasterize_points.cu:83: the reference skips everything and returns the
+        // zero-initialised outputs (NOT the background) and untouched empty blobs.
+        const size_t n = (size_t)width * height * sizeof(float);
+        cudaError_t e = cudaMemsetAsync(out_color, 0, 3 * n, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(out_depth, 0, n, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(out_alpha, 0, n, st);
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "zero outputs", e);
+        return B3GS_OK;
+    }
+
+    // image state
+    ImageLayout il(width, height);
+    char* img = static_cast<char*>(image.resize(image.user, il.total));
+    if (!img) return fail(B3GS_ERR_ALLOC, "b3gs_forward: image buffer allocation failed");
+    img = align_ptr(img);
+    uint32_t* n_contrib = reinterpret_cast<uint32_t*>(img + il.n_contrib);
+    uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
+
+    int R = 0;
+    GeomLayout gl(P);
+    char* geo = nullptr;
+    if (P > 0) {
+        if (!means3D || !opacities || !viewmatrix || !projmatrix || !cam_pos || !radii)
+            return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: null required input pointer");
+        if ((shs == nullptr) == (colors_precomp == nullptr))
+            return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: provide exactly one of shs / colors_precomp");
+        if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+            return fail(B3GS_ERR_INVALID_ARGUMENT,
+                        "b3gs_forward: provide exactly one of (scales, rotations) / cov3D_precomp");
+        if (shs && M < (D + 1) * (D + 1))
+            return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: M < (D+1)^2 SH coefficients");
+        geo = static_cast<char*>(geometry.resize(geometry.user, gl.total));
+        if (!geo) return fail(B3GS_ERR_ALLOC, "b3gs_forward: geometry buffer allocation failed");
+        geo = align_ptr(geo);
+
+        PreprocessArgs pa;
+        pa.P = P; pa.D = D; pa.M = M;
+        pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations;
+        pa.opacities = opacities; pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+        pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
+        pa.W = width; pa.H = height; pa.tan_fovx = tan_fovx; pa.tan_fovy = tan_fovy;
+        pa.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:223-224
+        pa.focal_x = width / (2.0f * tan_fovx);
+        pa.grid_x = grid_x; pa.grid_y = grid_y; pa.prefiltered = prefiltered;
+        pa.radii = radii;
+        pa.records = reinterpret_cast<float4*>(geo + gl.records);
+        pa.depths = reinterpret_cast<float*>(geo + gl.depths);
+        pa.tiles_touched = reinterpret_cast<uint32_t*>(geo + gl.tiles_touched);
+        pa.clamped = reinterpret_cast<uint8_t*>(geo + gl.clamped);
+        launch_preprocess(pa, st);
+        B3_CHECK_STAGE("preprocess");
+
+        uint32_t* offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
+        launch_inclusive_scan(pa.tiles_touched, offsets, reinterpret_cast<uint32_t*>(geo + gl.scan_scratch), P, st);
+        B3_CHECK_STAGE("scan");
+
+        // R = offsets[P-1]: one blocking read on OUR stream (rasterizer_impl.cu:282
+        // uses a device-wide cudaMemcpy).
+        int* hw = pinned_word();
+        if (!hw) return fail(B3GS_ERR_ALLOC, "b3gs_forward: pinned host word allocation failed");
+        cudaError_t e = cudaMemcpyAsync(hw, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "read num_rendered", e);
+        R = *hw;
+    }
+
+    BinLayout bl(R);
+    char* bin = static_cast<char*>(binning.resize(binning.user, bl.total));
+    if (!bin && bl.total > 0) return fail(B3GS_ERR_ALLOC, "b3gs_forward: binning buffer allocation failed");
+    bin = align_ptr(bin);
+    uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
+
+    {
+        BinningArgs ba;
+        ba.P = P; ba.R = R; ba.grid_x = grid_x; ba.grid_y = grid_y;
+        ba.records = geo ? reinterpret_cast<const float4*>(geo + gl.records) : nullptr;
+        ba.depths = geo ? reinterpret_cast<const float*>(geo + gl.depths) : nullptr;
+        ba.radii = radii;
+        ba.point_offsets = geo ? reinterpret_cast<const uint32_t*>(geo + gl.point_offsets) : nullptr;
+        ba.point_list = point_list;
+        ba.ranges = ranges;
+        ba.scratch = bin + bl.scratch;
+        ba.scratch_bytes = bl.scratch_bytes;
+        cudaError_t e = run_binning(ba, st);
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "binning", e);
+        B3_CHECK_STAGE("binning");
+    }
+
+    {
+        CompositeFwdArgs ca;
+        ca.W = width; ca.H = height; ca.grid_x = grid_x; ca.grid_y = grid_y;
+        ca.ranges = ranges; ca.point_list = point_list;
+        ca.records = geo ? reinterpret_cast<const float4*>(geo + gl.records) : nullptr;
+        ca.background = background;
+        ca.out_color = out_color; ca.out_depth = out_depth; ca.out_alpha = out_alpha; ca.n_contrib = n_contrib;
+        launch_composite_forward(ca, st);
+        B3_CHECK_STAGE("composite_forward");
+    }
+    if (num_rendered) *num_rendered = R;
+    return B3GS_OK;
+}
+
+int b3gs_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                  const float* means3D, const float* shs, const float* colors_precomp, const float* alphas,
+                  const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                  const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                  float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                  const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+                  float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                  float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || R < 0)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: bad sizes");
+    if (P == 0) return B3GS_OK;
+    if (!geom_buffer || !image_buffer || (!binning_buffer && R > 0))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null state buffer");
+    if (!dL_dpix || !dL_dpix_depth || !dL_dalphas || !alphas || !radii || !means3D || !background)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null required input pointer");
+    if (!dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_ddepth || !dL_dmean3D || !dL_dcov3D ||
+        !dL_dscale || !dL_drot || (M > 0 && shs && !dL_dsh))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null gradient output pointer");
+    const int grid_x = (width + B3_TILE_X - 1) / B3_TILE_X, grid_y = (height + B3_TILE_Y - 1) / B3_TILE_Y;
+
+    GeomLayout gl(P);
+    ImageLayout il(width, height);
+    BinLayout bl(R, /*with_scratch=*/false);
+    char* geo = align_ptr(geom_buffer);
+    char* img = align_ptr(image_buffer);
+    char* bin = binning_buffer ? align_ptr(binning_buffer) : nullptr;
+    float* grads = reinterpret_cast<float*>(geo + gl.grads);
+
+    cudaError_t e = cudaMemsetAsync(grads, 0, (size_t)P * B3_GRAD_STRIDE * sizeof(float), st);
+    if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "zero gradient accumulator", e);
+
+    if (R > 0) {
+        CompositeBwdArgs ca;
+        ca.W = width; ca.H = height; ca.grid_x = grid_x; ca.grid_y = grid_y;
+        ca.ranges = reinterpret_cast<const uint2*>(img + il.ranges);
+        ca.point_list = reinterpret_cast<const uint32_t*>(bin + bl.point_list);
+        ca.records = reinterpret_cast<const float4*>(geo + gl.records);
+        ca.colors_override = nullptr;  // records.c already holds colors_precomp when given
+        ca.background = background;
+        ca.alphas = alphas;
+        ca.n_contrib = reinterpret_cast<const uint32_t*>(img + il.n_contrib);
+        ca.dL_dpix = dL_dpix; ca.dL_dpix_depth = dL_dpix_depth; ca.dL_dalphas = dL_dalphas;
+        ca.grads = grads;
+        launch_composite_backward(ca, st);
+        B3_CHECK_STAGE("composite_backward");
+    }
+
+    PreBackwardArgs pa;
+    pa.P = P; pa.D = D; pa.M = M;
+    pa.means3D = means3D; pa.radii = radii; pa.shs = shs;
+    pa.clamped = reinterpret_cast<const uint8_t*>(geo + gl.clamped);
+    pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
+    pa.cov3D_precomp = cov3D_precomp; pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.campos = campos;
+    pa.focal_y = height / (2.0f * tan_fovy);
+    pa.focal_x = width / (2.0f * tan_fovx);
+    pa.tan_fovx = tan_fovx; pa.tan_fovy = tan_fovy;
+    pa.grads = grads;
+    pa.dL_dmean2D = dL_dmean2D; pa.dL_dconic = dL_dconic; pa.dL_dopacity = dL_dopacity; pa.dL_dcolor = dL_dcolor;
+    pa.dL_ddepth = dL_ddepth; pa.dL_dmean3D = dL_dmean3D; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
+    pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
+    launch_preprocess_backward(pa, st);
+    B3_CHECK_STAGE("preprocess_backward");
+    return B3GS_OK;
+}
+
+int b3gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/,
+                      unsigned char* present, void* stream) {
+    if (P < 0) return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_mark_visible: P < 0");
+    if (P == 0) return B3GS_OK;
+    if (!means3D || !viewmatrix || !present)
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_mark_visible: null pointer");
+    launch_mark_visible(P, means3D, viewmatrix, present, reinterpret_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "mark_visible", e);
+    return B3GS_OK;
+}
+
+size_t b3gs_geometry_bytes(int P) { return GeomLayout(P).total; }
+size_t b3gs_binning_bytes(int R) { return BinLayout(R).total; }
+size_t b3gs_image_bytes(int width, int height) { return ImageLayout(width, height).total; }
+
+size_t b3gs_geometry_offset(int P, const char* name) {
+    GeomLayout l(P);
+    if (!strcmp(name, "records")) return l.records;
+    if (!strcmp(name, "depths")) return l.depths;
+    if (!strcmp(name, "tiles_touched")) return l.tiles_touched;
+    if (!strcmp(name, "point_offsets")) return l.point_offsets;
+    if (!strcmp(name, "clamped")) return l.clamped;
+    if (!strcmp(name, "grads")) return l.grads;
+    return (size_t)-1;
+}
+size_t b3gs_binning_offset(int R, const char* name) {
+    BinLayout l(R);
+    if (!strcmp(name, "point_list")) return l.point_list;
+    return (size_t)-1;
+}
+size_t b3gs_image_offset(int width, int height, const char* name) {
+    ImageLayout l(width, height);
+    if (!strcmp(name, "n_contrib")) return l.n_contrib;
+    if (!strcmp(name, "ranges")) return l.ranges;
+    return (size_t)-1;
+}
+
+const char* b3gs_last_error(void) { return g_error.c_str(); }
+const char* b3gs_version(void) { return "b3gs 0.1 (sm_100a)"; }
+unsigned long long b3gs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// common.cuh — shared types and the reference-exact arithmetic primitives.
+//
+// The reference (diff-gaussian-rasterization, built by nvcc with the default
+// -fmad=true) does not compute what its C++ source literally says: ptxas contracts
+// multiplies and adds into FMAs in a specific pattern.  Tile keys embed
+// float_bits(depth) and the tile rectangle comes from ceil(3*sqrt(lambda)), so a
+// 1-ulp difference in the preprocess flips sort keys and radii.  The pattern below
+// was decoded from the reference's sm_100a SASS (profiles/ref_forward_sm100a.sass)
+// and is written with explicit round-to-nearest intrinsics so that neither nvcc
+// nor a future toolkit can re-associate it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B3_TILE_X 16
+#define B3_TILE_Y 16
+#define B3_TILE_PIXELS 256
+
+// Per-Gaussian record written by the preprocess and gathered by both composite
+// kernels: three 16-byte vectors, 48 B, so one Gaussian is three LDG.128.
+//   a = { x, y, ext_x, ext_y }   pixel-space mean and the conservative half-extents
+//                                of the region where alpha can reach 1/255
+//   b = { conic.x, conic.y, conic.z, opacity }
+//   c = { r, g, b, depth }
+#define B3_REC_VEC4 3
+#define B3_GRAD_STRIDE 12  // packed per-Gaussian gradient accumulator, floats
+
+// Layout of the packed gradient accumulator (one RED instruction per warp-survivor).
+#define B3_G_MEAN2D_X 0
+#define B3_G_MEAN2D_Y 1
+#define B3_G_CONIC_X 2
+#define B3_G_CONIC_Y 3
+#define B3_G_CONIC_W 4
+#define B3_G_OPACITY 5
+#define B3_G_COLOR_R 6
+#define B3_G_COLOR_G 7
+#define B3_G_COLOR_B 8
+#define B3_G_DEPTH 9
+
+namespace b3 {
+
+// a0*b0 + a1*b1 + a2*b2 as the reference's SASS evaluates it:
+// the MIDDLE product is rounded alone, then the first and the last are fused in.
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+
+// matrix[i]*x + matrix[i+4]*y + matrix[i+8]*z + matrix[i+12]  (auxiliary.h:58-77)
+__device__ __forceinline__ float xform(float m0, float m4, float m8, float m12, float x, float y, float z) {
+    return __fadd_rn(dot3(m0, x, m4, y, m8, z), m12);
+}
+
+// ((v + 1.0) * S - 1.0) * 0.5 in DOUBLE, rounded once to float (auxiliary.h:41-44;
+// SASS: F2F.F64.F32, DADD, DFMA, DMUL, F2F.F32.F64).
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    double d = __dadd_rn((double)v, 1.0);
+    d = __fma_rn(d, (double)S, -1.0);
+    d = __dmul_rn(d, 0.5);
+    return __double2float_rn(d);
+}
+
+// Tile rectangle (auxiliary.h:46-56): float arithmetic, truncation toward zero,
+// clamp to [0, grid].  `rf` is the radius already converted int -> float.
+__device__ __forceinline__ void tile_rect(float px, float py, float rf, int grid_x, int grid_y,
+                                          int& x0, int& y0, int& x1, int& y1) {
+    x0 = min(grid_x, max(0, __float2int_rz(__fmul_rn(__fsub_rn(px, rf), 0.0625f))));
+    y0 = min(grid_y, max(0, __float2int_rz(__fmul_rn(__fsub_rn(py, rf), 0.0625f))));
+    x1 = min(grid_x, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(px, rf), 16.0f), -1.0f), 0.0625f))));
+    y1 = min(grid_y, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(py, rf), 16.0f), -1.0f), 0.0625f))));
+}
+
+// Gaussian falloff exponent at pixel offset (dx,dy) (forward.cu:339, backward.cu:525).
+// SASS: s = fma(dx, dx*cx, dy*(dy*cz)); power = fma(s, -0.5, -(dy*(dx*cy))).
+__device__ __forceinline__ float gauss_power(float dx, float dy, float cx, float cy, float cz) {
+    float s = __fmaf_rn(dx, __fmul_rn(dx, cx), __fmul_rn(dy, __fmul_rn(dy, cz)));
+    return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cy)));
+}
+
+}  // namespace b3

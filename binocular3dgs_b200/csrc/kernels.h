@@ -1,0 +1,119 @@
+// kernels.h — host-side launch interface between api.cu and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b3 {
+
+void count_launch(unsigned n = 1);
+
+// ---------------------------------------------------------------- K1 / K10
+struct PreprocessArgs {
+    int P, D, M;
+    const float* means3D;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    int W, H;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int grid_x, grid_y;
+    int prefiltered;
+    int* radii;
+    float4* records;
+    float* depths;
+    uint32_t* tiles_touched;
+    uint8_t* clamped;
+};
+void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                         cudaStream_t stream);
+
+// ---------------------------------------------------------------- binning (K2-K5)
+// Inclusive prefix sum of tiles_touched -> point_offsets (u32), P elements.
+// `block_sums` is scratch of scan_scratch_elems(P) u32.
+size_t scan_scratch_elems(int P);
+void launch_inclusive_scan(const uint32_t* in, uint32_t* out, uint32_t* block_sums, int P, cudaStream_t stream);
+
+struct BinningArgs {
+    int P, R;
+    int grid_x, grid_y;
+    const float4* records;
+    const float* depths;
+    const int* radii;
+    const uint32_t* point_offsets;  // inclusive scan of tiles_touched
+    uint32_t* point_list;           // out: sorted Gaussian ids, R
+    uint2* ranges;                  // out: per-tile [start,end), T
+    char* scratch;                  // binning scratch (after point_list in the blob)
+    size_t scratch_bytes;
+};
+size_t binning_scratch_bytes(int R);
+cudaError_t run_binning(const BinningArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K6 / K7
+struct CompositeFwdArgs {
+    int W, H, grid_x, grid_y;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* records;
+    const float* background;
+    float* out_color;
+    float* out_depth;
+    float* out_alpha;
+    uint32_t* n_contrib;
+};
+void launch_composite_forward(const CompositeFwdArgs& a, cudaStream_t stream);
+
+struct CompositeBwdArgs {
+    int W, H, grid_x, grid_y;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* records;          // a/b from the forward; colours may be overridden
+    const float* colors_override;   // colors_precomp (P,3) or nullptr -> records.c.rgb
+    const float* background;
+    const float* alphas;            // forward out_alpha
+    const uint32_t* n_contrib;
+    const float* dL_dpix;           // [3,H,W]
+    const float* dL_dpix_depth;     // [H,W]
+    const float* dL_dalphas;        // [H,W]
+    float* grads;                   // [P, B3_GRAD_STRIDE], zeroed by the caller
+};
+void launch_composite_backward(const CompositeBwdArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K8 + K9 fused
+struct PreBackwardArgs {
+    int P, D, M;
+    const float* means3D;
+    const int* radii;
+    const float* shs;
+    const uint8_t* clamped;
+    const float* scales;
+    const float* rotations;
+    float scale_modifier;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float focal_x, focal_y, tan_fovx, tan_fovy;
+    const float* grads;  // packed accumulator from K7
+    float* dL_dmean2D;   // [P,3]
+    float* dL_dconic;    // [P,4]
+    float* dL_dopacity;  // [P]
+    float* dL_dcolor;    // [P,3]
+    float* dL_ddepth;    // [P]
+    float* dL_dmean3D;   // [P,3]
+    float* dL_dcov3D;    // [P,6]
+    float* dL_dsh;       // [P,M,3] or nullptr
+    float* dL_dscale;    // [P,3]
+    float* dL_drot;      // [P,4]
+};
+void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream);
+
+}  // namespace b3

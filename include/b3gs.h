@@ -1,0 +1,211 @@
+/*
+ * b3gs.h — C-ABI of the B200-native differentiable 3D Gaussian Splatting rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of hanl2010/Binocular3DGS: the
+ * differentiable rasterizer the reference reaches through
+ *   submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:20-90
+ *   (CudaRasterizer::Rasterizer::{markVisible, forward, backward})
+ * and binds to Python in
+ *   submodules/diff-gaussian-rasterization/rasterize_points.cu:35-229, ext.cpp:15-18.
+ *
+ * Every entry point below takes plain device pointers, sizes and a CUDA stream —
+ * no torch types — so the same shared library can be bound from ctypes (what
+ * binocular3dgs_b200/_backend.py does), pybind, cgo or JNI.  Argument order and
+ * meaning follow the reference interface each function replaces; the only
+ * additions are the trailing `stream` (the reference uses the legacy default
+ * stream everywhere, rasterizer_impl.cu:148,290,315) and the explicit
+ * `num_rendered` out-parameter / error return (the reference returns the count
+ * and throws std::runtime_error).
+ *
+ * All pointers are DEVICE pointers unless stated.  All floating point is FP32.
+ * "Optional" pointers follow the reference's null convention
+ * (rasterize_points.cu:96-115: empty tensors arrive as nullptr).
+ */
+#ifndef B3GS_H_INCLUDED
+#define B3GS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B3GS_API __attribute__((visibility("default")))
+#else
+#define B3GS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Tile geometry is part of observable behaviour (config.h:15-17): it fixes
+ * tiles_touched, the sort keys and the per-tile ranges. */
+#define B3GS_TILE_X 16
+#define B3GS_TILE_Y 16
+#define B3GS_NUM_CHANNELS 3
+
+/* Error codes (negative). 0 = success. */
+#define B3GS_OK 0
+#define B3GS_ERR_INVALID_ARGUMENT (-1)
+#define B3GS_ERR_CUDA (-2)
+#define B3GS_ERR_ALLOC (-3)
+
+/*
+ * Resize callback, the C form of the reference's
+ *   std::function<char*(size_t)>  (rasterizer.h:32-34, rasterize_points.cu:27-33).
+ * Must return a device pointer to at least `bytes` bytes, aligned to >= 128 B,
+ * that stays valid until the matching b3gs_backward call has been enqueued.
+ * `user` is passed back verbatim.  Returning NULL for bytes > 0 aborts the call
+ * with B3GS_ERR_ALLOC.
+ */
+typedef void* (*b3gs_resize_fn)(void* user, size_t bytes);
+
+typedef struct b3gs_buffer {
+    b3gs_resize_fn resize;
+    void* user;
+} b3gs_buffer;
+
+/*
+ * Forward rasterization.  Replaces CudaRasterizer::Rasterizer::forward
+ * (rasterizer.h:31-58, rasterizer_impl.cu:197-339).
+ *
+ *   geometry/binning/image : the three opaque state blobs (GeometryState,
+ *       BinningState, ImageState in the reference, rasterizer_impl.h:22-73).  Their
+ *       layout is private to this library but is a pure function of (P), (R) and
+ *       (width,height) respectively, so b3gs_backward can re-derive it.
+ *   P, D, M      : #Gaussians, active SH degree (0..3), SH coefficients per Gaussian
+ *                  in `shs` (0 when colours are precomputed).
+ *   background   : float[3].
+ *   means3D      : float[P,3].          shs : float[P,M,3] or NULL.
+ *   colors_precomp : float[P,3] or NULL (exactly one of shs / colors_precomp).
+ *   opacities    : float[P].            scales : float[P,3] or NULL.
+ *   rotations    : float[P,4] (r,x,y,z; NOT normalised here, forward.cu:127) or NULL.
+ *   cov3D_precomp: float[P,6] or NULL (exactly one of (scales,rotations) / cov3D).
+ *   viewmatrix, projmatrix : float[16], transposed (column-major) convention of
+ *                  scene/cameras.py:55-57.   cam_pos : float[3].
+ *   out_color    : float[3,H,W]; out_depth, out_alpha : float[H,W]; radii : int[P].
+ *                  Outputs need NOT be pre-zeroed (the reference requires zeros,
+ *                  rasterize_points.cu:68-71; here every element is written).
+ *   prefiltered  : as the reference (auxiliary.h:156-160): a culled point traps.
+ *   debug        : synchronise and check after every kernel (auxiliary.h:166-173).
+ *   stream       : cudaStream_t to enqueue on.
+ *   num_rendered : HOST int, receives R = number of (Gaussian,tile) instances.
+ *
+ * The call blocks the host once, on `stream`, to read R (the reference blocks the
+ * whole device with cudaMemcpy, rasterizer_impl.cu:282).
+ */
+B3GS_API int b3gs_forward(
+    b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    float* out_alpha,
+    int* radii,
+    int debug,
+    void* stream,
+    int* num_rendered);
+
+/*
+ * Backward.  Replaces CudaRasterizer::Rasterizer::backward
+ * (rasterizer.h:60-89, rasterizer_impl.cu:343-447).  Argument order follows the
+ * reference.  `alphas` is the forward's out_alpha.  Gradient outputs:
+ *   dL_dmean2D float[P,3] (x,y used; z written 0), dL_dconic float[P,4] (x,y,-,w),
+ *   dL_dopacity float[P], dL_dcolor float[P,3], dL_ddepth float[P],
+ *   dL_dmean3D float[P,3], dL_dcov3D float[P,6], dL_dsh float[P,M,3] (or NULL when
+ *   M==0), dL_dscale float[P,3], dL_drot float[P,4].
+ * Unlike the reference (rasterize_points.cu:158-167) the outputs need NOT be
+ * pre-zeroed: every element is written by this call.
+ */
+B3GS_API int b3gs_backward(
+    int P, int D, int M, int R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* alphas,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer,
+    char* binning_buffer,
+    char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    const float* dL_dalphas,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_ddepth,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    int debug,
+    void* stream);
+
+/* Visibility mask.  Replaces Rasterizer::markVisible (rasterizer.h:24-29,
+ * rasterizer_impl.cu:54-66,141-153): present[i] = (z_view > 0.2). `present` is
+ * bool[P] (1 byte each). */
+B3GS_API int b3gs_mark_visible(
+    int P,
+    const float* means3D,
+    const float* viewmatrix,
+    const float* projmatrix,
+    unsigned char* present,
+    void* stream);
+
+/* Sizes of the three opaque blobs (what the resize callbacks will be asked for).
+ * Pure functions of their arguments. */
+B3GS_API size_t b3gs_geometry_bytes(int P);
+B3GS_API size_t b3gs_binning_bytes(int R);
+B3GS_API size_t b3gs_image_bytes(int width, int height);
+
+/*
+ * Introspection for parity tests (the analogue of slicing the reference's blobs,
+ * SURVEY.md §8c): byte offsets of named arrays inside the blobs.  Returns the
+ * offset, or (size_t)-1 for an unknown name.
+ *   geometry: "depths" f32[P], "tiles_touched" u32[P], "point_offsets" u32[P],
+ *             "records" f32[P,12] = {x, y, ext_x, ext_y | conic_x, conic_y, conic_z,
+ *             opacity | r, g, b, depth}, "clamped" u8[P] (bit c = channel c clamped)
+ *   binning:  "point_list" u32[R]
+ *   image:    "n_contrib" u32[H*W], "ranges" u32[T,2]
+ */
+B3GS_API size_t b3gs_geometry_offset(int P, const char* name);
+B3GS_API size_t b3gs_binning_offset(int R, const char* name);
+B3GS_API size_t b3gs_image_offset(int width, int height, const char* name);
+
+/* Last error message of the calling thread ("" if none). */
+B3GS_API const char* b3gs_last_error(void);
+
+/* Library version string, and the number of kernels this library launched since
+ * load (used by bench.py to report gpu_launches). */
+B3GS_API const char* b3gs_version(void);
+B3GS_API unsigned long long b3gs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B3GS_H_INCLUDED */
