@@ -110,6 +110,17 @@ class Backend:
             f.restype = ctypes.c_size_t
             f.argtypes = [ctypes.c_int, ctypes.c_int] if kind == "image" else [ctypes.c_int]
             setattr(self, "_" + kind + "_bytes", f)
+        # per-stage device timing (only our library implements it)
+        self.has_profile = hasattr(self.lib, prefix + "profile_read")
+        if self.has_profile:
+            g("profile_enable").argtypes = [ctypes.c_int]
+            g("profile_stage_name").restype = ctypes.c_char_p
+            g("profile_stage_name").argtypes = [ctypes.c_int]
+            g("profile_read").argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+        # Optional dict name -> preallocated tensor ("means3D", "shs", "opacities", "scales",
+        # "rotations") the backward writes its parameter gradients INTO instead of
+        # allocating them — how dp.GradientBucket receives gradients without a pack copy.
+        self.grad_sink = None
         # One persistent C callback; `user` is the slot index (0 geom, 1 binning, 2 image).
         self._tls = threading.local()
         self._cb = _RESIZE_FN(self._resize)
@@ -120,6 +131,21 @@ class Backend:
 
     def launch_count(self) -> int:
         return int(self._launch_count())
+
+    def profile_enable(self, on: bool):
+        if self.has_profile:
+            getattr(self.lib, self.prefix + "profile_enable")(int(bool(on)))
+
+    def profile_read(self):
+        """{stage: (device_ms_total, calls)} since the last read; waits for the events."""
+        if not self.has_profile:
+            return {}
+        n = getattr(self.lib, self.prefix + "profile_num_stages")()
+        ms = (ctypes.c_double * n)()
+        calls = (ctypes.c_ulonglong * n)()
+        getattr(self.lib, self.prefix + "profile_read")(ms, calls, n)
+        name = getattr(self.lib, self.prefix + "profile_stage_name")
+        return {name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
 
     def _err(self, what: str, code: int) -> RuntimeError:
         return RuntimeError(f"{self.name}.{what} failed ({code}): {self._last_error().decode()}")
@@ -213,6 +239,20 @@ class Backend:
             dL_dsh = alloc((P, M, 3), **o)
             dL_dscales = alloc((P, 3), **o)
             dL_drotations = alloc((P, 4), **o)
+            sink = self.grad_sink
+            if sink is not None and P != 0:
+                def take(name, t):
+                    v = sink.get(name)
+                    if v is None or v.numel() != t.numel() or v.device != t.device or not v.is_contiguous():
+                        return t
+                    if self.needs_zeroed_outputs:
+                        v.zero_()
+                    return v.view(t.shape)
+                dL_dmeans3D = take("means3D", dL_dmeans3D)
+                dL_dsh = take("shs", dL_dsh)
+                dL_dopacity = take("opacities", dL_dopacity)
+                dL_dscales = take("scales", dL_dscales)
+                dL_drotations = take("rotations", dL_drotations)
             if P != 0:
                 bg, m3, col, sca, rot, cov, vm, pm, shs, cam, alp, gc, gd, ga = (
                     _prep(background, "background"), _prep(means3D, "means3D"), _prep(colors, "colors_precomp"),

@@ -8,7 +8,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/b3gs.h"
 #include "common.cuh"
@@ -84,6 +86,44 @@ static int* pinned_word() {
     }
     return w;
 }
+
+// ---- optional per-stage device timing (bench.py roofline) ---------------------
+// When enabled, every stage is bracketed by a pair of CUDA events recorded on the
+// caller's stream; b3gs_profile_read() synchronises on them and sums the elapsed
+// device time per stage.  Disabled: zero overhead (one relaxed atomic load).
+enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_BINNING, ST_COMPOSITE_FWD, ST_GRAD_ZERO, ST_COMPOSITE_BWD,
+             ST_PREPROCESS_BWD, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "binning", "composite_forward", "grad_zero",
+                                            "composite_backward", "preprocess_backward"};
+struct ProfPair { int stage; cudaEvent_t a, b; };
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfPair> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {
+    bool on; int stage; cudaStream_t st; cudaEvent_t a, b;
+    StageTimer(int stage_, cudaStream_t st_) : on(g_profile.load(std::memory_order_relaxed) != 0), stage(stage_), st(st_) {
+        if (on) {
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            a = prof_event(); b = prof_event();
+            cudaEventRecord(a, st);
+        }
+    }
+    ~StageTimer() {
+        if (on) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof_pending.push_back({stage, a, b});
+        }
+    }
+};
 
 #define B3_CHECK_STAGE(what)                                             \
     do {                                                                 \
@@ -165,11 +205,17 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         pa.depths = reinterpret_cast<float*>(geo + gl.depths);
         pa.tiles_touched = reinterpret_cast<uint32_t*>(geo + gl.tiles_touched);
         pa.clamped = reinterpret_cast<uint8_t*>(geo + gl.clamped);
-        launch_preprocess(pa, st);
+        {
+            StageTimer t_(ST_PREPROCESS, st);
+            launch_preprocess(pa, st);
+        }
         B3_CHECK_STAGE("preprocess");
 
         uint32_t* offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
-        launch_inclusive_scan(pa.tiles_touched, offsets, reinterpret_cast<uint32_t*>(geo + gl.scan_scratch), P, st);
+        {
+            StageTimer t_(ST_SCAN, st);
+            launch_inclusive_scan(pa.tiles_touched, offsets, reinterpret_cast<uint32_t*>(geo + gl.scan_scratch), P, st);
+        }
         B3_CHECK_STAGE("scan");
 
         // R = offsets[P-1]: one blocking read on OUR stream (rasterizer_impl.cu:282
@@ -199,7 +245,11 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         ba.ranges = ranges;
         ba.scratch = bin + bl.scratch;
         ba.scratch_bytes = bl.scratch_bytes;
-        cudaError_t e = run_binning(ba, st);
+        cudaError_t e;
+        {
+            StageTimer t_(ST_BINNING, st);
+            e = run_binning(ba, st);
+        }
         if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "binning", e);
         B3_CHECK_STAGE("binning");
     }
@@ -211,7 +261,10 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         ca.records = geo ? reinterpret_cast<const float4*>(geo + gl.records) : nullptr;
         ca.background = background;
         ca.out_color = out_color; ca.out_depth = out_depth; ca.out_alpha = out_alpha; ca.n_contrib = n_contrib;
-        launch_composite_forward(ca, st);
+        {
+            StageTimer t_(ST_COMPOSITE_FWD, st);
+            launch_composite_forward(ca, st);
+        }
         B3_CHECK_STAGE("composite_forward");
     }
     if (num_rendered) *num_rendered = R;
@@ -247,7 +300,11 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
     char* bin = binning_buffer ? align_ptr(binning_buffer) : nullptr;
     float* grads = reinterpret_cast<float*>(geo + gl.grads);
 
-    cudaError_t e = cudaMemsetAsync(grads, 0, (size_t)P * B3_GRAD_STRIDE * sizeof(float), st);
+    cudaError_t e;
+    {
+        StageTimer t_(ST_GRAD_ZERO, st);
+        e = cudaMemsetAsync(grads, 0, (size_t)P * B3_GRAD_STRIDE * sizeof(float), st);
+    }
     if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "zero gradient accumulator", e);
 
     if (R > 0) {
@@ -262,7 +319,10 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
         ca.n_contrib = reinterpret_cast<const uint32_t*>(img + il.n_contrib);
         ca.dL_dpix = dL_dpix; ca.dL_dpix_depth = dL_dpix_depth; ca.dL_dalphas = dL_dalphas;
         ca.grads = grads;
-        launch_composite_backward(ca, st);
+        {
+            StageTimer t_(ST_COMPOSITE_BWD, st);
+            launch_composite_backward(ca, st);
+        }
         B3_CHECK_STAGE("composite_backward");
     }
 
@@ -279,7 +339,10 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
     pa.dL_dmean2D = dL_dmean2D; pa.dL_dconic = dL_dconic; pa.dL_dopacity = dL_dopacity; pa.dL_dcolor = dL_dcolor;
     pa.dL_ddepth = dL_ddepth; pa.dL_dmean3D = dL_dmean3D; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
     pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
-    launch_preprocess_backward(pa, st);
+    {
+        StageTimer t_(ST_PREPROCESS_BWD, st);
+        launch_preprocess_backward(pa, st);
+    }
     B3_CHECK_STAGE("preprocess_backward");
     return B3GS_OK;
 }
@@ -320,6 +383,31 @@ size_t b3gs_image_offset(int width, int height, const char* name) {
     if (!strcmp(name, "n_contrib")) return l.n_contrib;
     if (!strcmp(name, "ranges")) return l.ranges;
     return (size_t)-1;
+}
+
+void b3gs_profile_enable(int on) { g_profile.store(on ? 1 : 0, std::memory_order_relaxed); }
+int b3gs_profile_num_stages(void) { return ST_COUNT; }
+const char* b3gs_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int b3gs_profile_read(double* ms_total, unsigned long long* calls, int n) {
+    std::vector<ProfPair> pend;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        pend.swap(g_prof_pending);
+    }
+    for (int i = 0; i < n; i++) { ms_total[i] = 0.0; calls[i] = 0; }
+    for (auto& p : pend) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess &&
+            p.stage < n) {
+            ms_total[p.stage] += ms;
+            calls[p.stage] += 1;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        for (auto& p : pend) { g_prof_pool.push_back(p.a); g_prof_pool.push_back(p.b); }
+    }
+    return (int)pend.size();
 }
 
 const char* b3gs_last_error(void) { return g_error.c_str(); }

@@ -1,0 +1,82 @@
+"""View-parallel data parallelism for the rasterizer hot path.
+
+The reference has no collective of any kind: its multi-GPU story is one independent
+``train.py`` per scene per GPU (``script/run_llff.py:21-37,61-98``).  A rasterizer call
+is a pure function of (Gaussians, camera), so the path shards by VIEW: every rank holds
+a replica of the Gaussians, renders its own camera, and the per-Gaussian gradients are
+summed with ONE in-place all-reduce over a flat FP32 bucket.
+
+``GradientBucket`` is that bucket.  Its segments are laid out
+``[means3D 3 | sh 3M | opacity 1 | scales 3 | rotations 4]`` × P as five contiguous
+arrays, and the tensors handed out by :meth:`views` alias it, so when the backward of
+the operator writes its outputs *into* those views (``Backend.grad_sink``) there is no
+pack/copy step between the backward kernel and NCCL: the kernel's stores are the
+collective's send buffer.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+SEGMENTS = ("means3D", "shs", "opacities", "scales", "rotations")
+
+
+class GradientBucket:
+    def __init__(self, P: int, M: int, device, dtype=torch.float32):
+        self.P, self.M = int(P), int(M)
+        self.widths = {"means3D": 3, "shs": 3 * self.M, "opacities": 1, "scales": 3, "rotations": 4}
+        self.floats_per_gaussian = sum(self.widths.values())  # 11 + 3M
+        self.flat = torch.zeros(self.P * self.floats_per_gaussian, dtype=dtype, device=device)
+        self._views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name in SEGMENTS:
+            n = self.P * self.widths[name]
+            v = self.flat[off:off + n]
+            shape = (self.P, self.M, 3) if name == "shs" else (self.P, self.widths[name])
+            self._views[name] = v.view(shape)
+            off += n
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        """Tensors aliasing the bucket, one per parameter group."""
+        return self._views
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def load(self, grads: Dict[str, torch.Tensor]):
+        """Copy gradients in (only needed when the backward did not write in place)."""
+        for name in SEGMENTS:
+            g = grads[name]
+            if g.data_ptr() != self._views[name].data_ptr():
+                self._views[name].copy_(g.reshape(self._views[name].shape))
+
+    def all_reduce(self, group=None, average: bool = True, async_op: bool = False):
+        """Sum (or average) the bucket over the ranks of ``group``; in place."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if average and not async_op:
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+        return work
+
+
+def shard_views(num_views: int, rank: int, world_size: int):
+    """Indices of the views rank ``rank`` renders this step: view v goes to rank v % N."""
+    return list(range(rank, num_views, world_size))
+
+
+def reduce_densify_stats(grad_norm: torch.Tensor, visible: torch.Tensor, max_radii: torch.Tensor, group=None):
+    """Statistics that must NOT be derived from the reduced gradient:
+    the densifier uses the per-view NORM of dL/dmean2D and a visibility count
+    (scene/gaussian_model.py:409-411) and the max screen radius (train.py:178).  Each
+    rank contributes its own norm / count, summed; radii are max-reduced."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return grad_norm, visible, max_radii
+    packed = torch.stack([grad_norm.reshape(-1).float(), visible.reshape(-1).float()], dim=0)
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    r = max_radii.clone()
+    dist.all_reduce(r, op=dist.ReduceOp.MAX, group=group)
+    return packed[0].reshape(grad_norm.shape), packed[1].reshape(visible.shape), r

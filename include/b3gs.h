@@ -197,6 +197,19 @@ B3GS_API size_t b3gs_geometry_offset(int P, const char* name);
 B3GS_API size_t b3gs_binning_offset(int R, const char* name);
 B3GS_API size_t b3gs_image_offset(int width, int height, const char* name);
 
+/*
+ * Optional per-stage device timing, used by bench.py for the roofline figures.  When
+ * enabled every stage (preprocess, scan, binning, composite_forward, grad_zero,
+ * composite_backward, preprocess_backward) is bracketed by CUDA events on the caller's
+ * stream.  b3gs_profile_read() waits for the recorded events, writes the summed
+ * device milliseconds and the number of calls per stage into ms_total[n] / calls[n],
+ * clears the record and returns the number of (stage, call) samples consumed.
+ */
+B3GS_API void b3gs_profile_enable(int on);
+B3GS_API int b3gs_profile_num_stages(void);
+B3GS_API const char* b3gs_profile_stage_name(int i);
+B3GS_API int b3gs_profile_read(double* ms_total, unsigned long long* calls, int n);
+
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
 
