@@ -206,7 +206,8 @@ def test_sh_degrees_with_16_coefficients(deg, nat, dev):
                                         tuple(t.to(dev) for t in make_pixel_grads(W, H)))
     assert np.abs(out["color"].cpu().numpy() - of["color"]).max() <= 1e-5
     n = (deg + 1) ** 2
-    assert float(out["g_shs"][:, n:, :].abs().max()) == 0      # untouched coefficients get exact zeros
+    if n < 16:
+        assert float(out["g_shs"][:, n:, :].abs().max()) == 0  # untouched coefficients get exact zeros
     assert float(out["g_shs"][:, :n, :].abs().max()) > 0
 
 
