@@ -289,8 +289,10 @@ def main():
         D = scene.sh_degree
         alg = {  # algorithmic bytes per launch, SURVEY.md §8(d)
             "preprocess": P * (44 + 12 * (D + 1) ** 2) + 75 * P,
-            "scan": 8 * P,
-            "binning": 20 * P + 12 * R + 152 * R + 8 * R + 8 * T,
+            # 4 passes x (4 B hist read + 8 B read + 8 B write) + gather-scan of tiles_touched
+            "depth_sort": P * (4 * 20 + 16),
+            # emit (tile,id) 8 B + passes x 20 B + 4 B boundary scan per instance, 8 B per tile
+            "binning": 28 * P + R * (8 + 20 * (1 if T <= 256 else 2 if T <= 65536 else 3) + 4) + 8 * T,
             "composite_forward": 44 * I_f + 8 * T + 24 * N,
             "grad_zero": 48 * P,
             "composite_backward": 44 * I_f + 8 * T + 28 * N + 80 * I_f,

@@ -36,17 +36,21 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- blob layouts: pure functions of (P), (R), (W,H) --------------------------
 struct GeomLayout {
-    size_t records, depths, tiles_touched, point_offsets, clamped, grads, scan_scratch, total;
+    size_t records, depths, tiles_touched, sorted_ids, point_offsets, clamped, counter, grads, scratch, total;
     explicit GeomLayout(int P) {
         const size_t p = (size_t)(P > 0 ? P : 0);
         size_t o = 0;
         records = o;       o = align_up(o + p * 48, 256);
         depths = o;        o = align_up(o + p * 4, 256);
         tiles_touched = o; o = align_up(o + p * 4, 256);
-        point_offsets = o; o = align_up(o + p * 4, 256);
+        sorted_ids = o;    o = align_up(o + p * 4, 256);   // Gaussian ids in (depth bits, id) order
+        point_offsets = o; o = align_up(o + p * 4, 256);   // exclusive scan of tiles_touched in that order
         clamped = o;       o = align_up(o + p, 256);
+        counter = o;       o = align_up(o + 16, 256);      // R accumulated by the preprocess
         grads = o;         o = align_up(o + p * B3_GRAD_STRIDE * 4, 256);
-        scan_scratch = o;  o = align_up(o + scan_scratch_elems(P) * 4, 256);
+        // Phase-1 sort scratch is dead once the forward returns; the backward's packed
+        // gradient accumulator could alias it, kept separate for clarity (P-sized, small).
+        scratch = o;       o = align_up(o + binning_phase1_scratch_bytes(P), 256);
         total = o + 256;
     }
 };
@@ -68,7 +72,7 @@ struct BinLayout {
         size_t o = 0;
         point_list = o; o = align_up(o + r * 4, 256);
         scratch = o;
-        scratch_bytes = with_scratch ? binning_scratch_bytes(R) : 0;
+        scratch_bytes = with_scratch ? binning_phase2_scratch_bytes(R) : 0;
         o = align_up(o + scratch_bytes, 256);
         total = o + 256;
     }
@@ -76,6 +80,15 @@ struct BinLayout {
 
 static char* align_ptr(void* p) {
     return reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
+}
+
+// One event per host thread: "R has landed in the pinned word".
+static cudaEvent_t count_event() {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) {
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    }
+    return ev;
 }
 
 // One pinned word per host thread for the R read-back.
@@ -93,7 +106,7 @@ static int* pinned_word() {
 // device time per stage.  Disabled: zero overhead (one relaxed atomic load).
 enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_BINNING, ST_COMPOSITE_FWD, ST_GRAD_ZERO, ST_COMPOSITE_BWD,
              ST_PREPROCESS_BWD, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "binning", "composite_forward", "grad_zero",
+static const char* kStageNames[ST_COUNT] = {"preprocess", "depth_sort", "binning", "composite_forward", "grad_zero",
                                             "composite_backward", "preprocess_backward"};
 struct ProfPair { int stage; cudaEvent_t a, b; };
 static std::atomic<int> g_profile{0};
@@ -205,26 +218,40 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         pa.depths = reinterpret_cast<float*>(geo + gl.depths);
         pa.tiles_touched = reinterpret_cast<uint32_t*>(geo + gl.tiles_touched);
         pa.clamped = reinterpret_cast<uint8_t*>(geo + gl.clamped);
+        pa.num_rendered = reinterpret_cast<uint32_t*>(geo + gl.counter);
+        cudaError_t e = cudaMemsetAsync(pa.num_rendered, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "zero instance counter", e);
         {
             StageTimer t_(ST_PREPROCESS, st);
             launch_preprocess(pa, st);
         }
         B3_CHECK_STAGE("preprocess");
 
-        uint32_t* offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
-        {
-            StageTimer t_(ST_SCAN, st);
-            launch_inclusive_scan(pa.tiles_touched, offsets, reinterpret_cast<uint32_t*>(geo + gl.scan_scratch), P, st);
-        }
-        B3_CHECK_STAGE("scan");
-
-        // R = offsets[P-1]: one blocking read on OUR stream (rasterizer_impl.cu:282
-        // uses a device-wide cudaMemcpy).
+        // R is needed on the host to size the binning blob (and is part of the operator
+        // surface).  Start its copy now, then enqueue the P-sized half of the binning, and
+        // only then wait: the GPU sorts by depth while the host sleeps on the event and
+        // allocates.  (rasterizer_impl.cu:282 blocks the whole device with cudaMemcpy.)
         int* hw = pinned_word();
-        if (!hw) return fail(B3GS_ERR_ALLOC, "b3gs_forward: pinned host word allocation failed");
-        cudaError_t e = cudaMemcpyAsync(hw, offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaEvent_t ev = count_event();
+        if (!hw || !ev) return fail(B3GS_ERR_ALLOC, "b3gs_forward: pinned word / event allocation failed");
+        e = cudaMemcpyAsync(hw, pa.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, st);
         if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "read num_rendered", e);
+
+        {
+            BinningPhase1Args b1;
+            b1.P = P; b1.depths = pa.depths; b1.tiles_touched = pa.tiles_touched;
+            b1.sorted_ids = reinterpret_cast<uint32_t*>(geo + gl.sorted_ids);
+            b1.sorted_offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
+            b1.scratch = geo + gl.scratch;
+            StageTimer t_(ST_SCAN, st);
+            e = run_binning_phase1(b1, st);
+        }
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "binning phase 1", e);
+        B3_CHECK_STAGE("binning phase 1");
+
+        e = cudaEventSynchronize(ev);
+        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "wait for num_rendered", e);
         R = *hw;
     }
 
@@ -235,20 +262,20 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
     uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
 
     {
-        BinningArgs ba;
+        BinningPhase2Args ba;
         ba.P = P; ba.R = R; ba.grid_x = grid_x; ba.grid_y = grid_y;
-        ba.records = geo ? reinterpret_cast<const float4*>(geo + gl.records) : nullptr;
-        ba.depths = geo ? reinterpret_cast<const float*>(geo + gl.depths) : nullptr;
+        ba.records = reinterpret_cast<const float4*>(geo + gl.records);
+        ba.depths = reinterpret_cast<const float*>(geo + gl.depths);
         ba.radii = radii;
-        ba.point_offsets = geo ? reinterpret_cast<const uint32_t*>(geo + gl.point_offsets) : nullptr;
+        ba.sorted_ids = reinterpret_cast<const uint32_t*>(geo + gl.sorted_ids);
+        ba.sorted_offsets = reinterpret_cast<const uint32_t*>(geo + gl.point_offsets);
         ba.point_list = point_list;
         ba.ranges = ranges;
         ba.scratch = bin + bl.scratch;
-        ba.scratch_bytes = bl.scratch_bytes;
         cudaError_t e;
         {
             StageTimer t_(ST_BINNING, st);
-            e = run_binning(ba, st);
+            e = run_binning_phase2(ba, st);
         }
         if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "binning", e);
         B3_CHECK_STAGE("binning");
@@ -258,7 +285,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         CompositeFwdArgs ca;
         ca.W = width; ca.H = height; ca.grid_x = grid_x; ca.grid_y = grid_y;
         ca.ranges = ranges; ca.point_list = point_list;
-        ca.records = geo ? reinterpret_cast<const float4*>(geo + gl.records) : nullptr;
+        ca.records = reinterpret_cast<const float4*>(geo + gl.records);
         ca.background = background;
         ca.out_color = out_color; ca.out_depth = out_depth; ca.out_alpha = out_alpha; ca.n_contrib = n_contrib;
         {
@@ -369,6 +396,7 @@ size_t b3gs_geometry_offset(int P, const char* name) {
     if (!strcmp(name, "depths")) return l.depths;
     if (!strcmp(name, "tiles_touched")) return l.tiles_touched;
     if (!strcmp(name, "point_offsets")) return l.point_offsets;
+    if (!strcmp(name, "sorted_ids")) return l.sorted_ids;
     if (!strcmp(name, "clamped")) return l.clamped;
     if (!strcmp(name, "grads")) return l.grads;
     return (size_t)-1;

@@ -1,25 +1,44 @@
-// binning.cu — K2..K5: prefix sum, (tile|depth) key emission, sort, tile ranges.
+// binning.cu — K2..K5: depth order, (tile, id) instance emission, tile sort, tile ranges.
 //
 // Reference behaviour: rasterizer_impl.cu:70-111 (duplicateWithKeys), :116-138
-// (identifyTileRanges), :35-50 (getHigherMsb), :278 (InclusiveSum), :304-309
-// (SortPairs on bits [0, 32+bit)), :311 (memset ranges).
+// (identifyTileRanges), :35-50 (getHigherMsb), :278 (cub InclusiveSum), :304-309
+// (cub SortPairs of 64-bit keys on bits [0, 32+bit)), :311 (memset ranges).
 //
 // Output contract (bit-exact): point_list[R] ordered by (tile id, float_bits(depth),
 // Gaussian index) and ranges[T] = [start,end) of each tile in that list, (0,0) for
-// empty tiles.
+// empty tiles.  The reference gets it from one stable LSD radix sort of R 64-bit keys
+// (6 onesweep passes, ~152 B/instance).  Any algorithm producing that total order is
+// equivalent, so this file uses the structure of the key instead:
 //
-// Round-1 state: the prefix sum, key emission and range detection are hand-written;
-// the 64-bit key sort still calls cub::DeviceRadixSort (library code, same call the
-// reference makes) — its replacement by the depth-presorted two-pass tile sort
-// described in DESIGN.md is the next step on this file.
+//   phase 1 (P-sized, runs while the host waits for R):
+//     stable LSD sort of the P Gaussians by float_bits(depth)        4 x 8-bit passes
+//     exclusive scan of tiles_touched in that order                   -> emission offsets
+//   phase 2 (R-sized):
+//     emit (tile, id) instances in depth order, one warp per 32 Gaussians
+//     stable LSD sort of the instances by tile id                     ceil(bits(T)/8) passes
+//     tile ranges from the sorted tile ids
+//
+// A stable sort by tile of a sequence already ordered by (depth bits, index) IS the
+// order (tile, depth bits, index).  The R-sized work drops from 6 passes over 12-byte
+// pairs to 2 passes over 8-byte pairs.  All passes are hand-written: per-block digit
+// histograms, a row scan, and a rank-and-scatter kernel that ranks with
+// __match_any_sync, reorders through shared memory and writes coalesced runs.  No
+// spin-waiting anywhere (three plain kernels per pass), so a bug cannot hang the GPU.
+//
+// The cub path the first revision used is kept behind B3GS_BINNING=cub for A/B timing.
 #include <cub/device/device_radix_sort.cuh>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.h"
 
 namespace b3 {
 
-// ------------------------------------------------------------------ prefix sum
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ block scans
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
@@ -33,25 +52,29 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
     return v;
 }
 
-// Block-wide inclusive scan of one value per thread; returns the inclusive value,
-// `total` = block sum.
+// Block-wide inclusive scan of one value per thread (blockDim.x multiple of 32, <= 1024).
 __device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
     uint32_t inc = warp_inclusive_scan(v, lane);
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+        uint32_t w = (lane < nwarps) ? s_warp[lane] : 0;
         w = warp_inclusive_scan(w, lane);
         s_warp[lane] = w;
     }
     __syncthreads();
     uint32_t prefix = warp > 0 ? s_warp[warp - 1] : 0;
-    total = s_warp[(blockDim.x >> 5) - 1];
+    total = s_warp[nwarps - 1];
+    __syncthreads();  // s_warp may be reused by the caller
     return inc + prefix;
 }
 
+// ------------------------------------------------------------------ exclusive scan with gather
+// out[i] = sum_{j<i} in[idx[j]]  (idx == nullptr: in[j]); total written to *total_out.
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in,
+                                                              const uint32_t* __restrict__ idx,
                                                               uint32_t* __restrict__ sums, int n) {
     __shared__ uint32_t s_warp[32];
     const int base = blockIdx.x * kScanTile;
@@ -59,15 +82,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* _
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
         int j = base + i * kScanThreads + threadIdx.x;
-        if (j < n) acc += in[j];
+        if (j < n) acc += idx ? in[idx[j]] : in[j];
     }
     uint32_t total;
     block_inclusive_scan(acc, s_warp, total);
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-// Single block: exclusive scan of the tile sums in place.
-__global__ void __launch_bounds__(1024) scan_sums_exclusive(uint32_t* __restrict__ sums, int m) {
+__global__ void __launch_bounds__(1024) scan_sums_exclusive(uint32_t* __restrict__ sums, int m,
+                                                           uint32_t* __restrict__ total_out) {
     __shared__ uint32_t s_warp[32];
     uint32_t carry = 0;
     for (int base = 0; base < m; base += 1024) {
@@ -77,21 +100,21 @@ __global__ void __launch_bounds__(1024) scan_sums_exclusive(uint32_t* __restrict
         uint32_t inc = block_inclusive_scan(v, s_warp, total);
         if (j < m) sums[j] = carry + inc - v;
         carry += total;
-        __syncthreads();
     }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in,
-                                                          const uint32_t* __restrict__ sums,
-                                                          uint32_t* __restrict__ out, int n) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply_exclusive(const uint32_t* __restrict__ in,
+                                                                    const uint32_t* __restrict__ idx,
+                                                                    const uint32_t* __restrict__ sums,
+                                                                    uint32_t* __restrict__ out, int n) {
     __shared__ uint32_t s_warp[32];
-    // blocked arrangement: thread t owns items [t*8, t*8+8) of the tile
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;  // blocked arrangement
     uint32_t v[kScanItems];
     uint32_t acc = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
-        v[i] = (base + i < n) ? in[base + i] : 0;
+        v[i] = (base + i < n) ? (idx ? in[idx[base + i]] : in[base + i]) : 0;
         acc += v[i];
     }
     uint32_t total;
@@ -99,57 +122,242 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __res
     uint32_t run = sums[blockIdx.x] + inc - acc;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
-        run += v[i];
         if (base + i < n) out[base + i] = run;
+        run += v[i];
     }
 }
 
-size_t scan_scratch_elems(int P) { return (size_t)((P + kScanTile - 1) / kScanTile) + 1; }
+static size_t scan_tiles(int n) { return (size_t)((n + kScanTile - 1) / kScanTile); }
 
-void launch_inclusive_scan(const uint32_t* in, uint32_t* out, uint32_t* block_sums, int P, cudaStream_t stream) {
-    const int tiles = (P + kScanTile - 1) / kScanTile;
-    scan_tile_sums<<<tiles, kScanThreads, 0, stream>>>(in, block_sums, P);
-    scan_sums_exclusive<<<1, 1024, 0, stream>>>(block_sums, tiles);
-    scan_apply<<<tiles, kScanThreads, 0, stream>>>(in, block_sums, out, P);
+static void exclusive_scan_gather(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* sums,
+                                  uint32_t* total_out, int n, cudaStream_t stream) {
+    const int tiles = (int)scan_tiles(n);
+    scan_tile_sums<<<tiles, kScanThreads, 0, stream>>>(in, idx, sums, n);
+    scan_sums_exclusive<<<1, 1024, 0, stream>>>(sums, tiles, total_out);
+    scan_apply_exclusive<<<tiles, kScanThreads, 0, stream>>>(in, idx, sums, out, n);
     count_launch(3);
 }
 
-// ------------------------------------------------------------------ key emission
-// One (key,value) per (Gaussian, tile) overlap, rows then columns of the rectangle
-// (rasterizer_impl.cu:98-108).  key = tile_id << 32 | float_bits(depth).
-__global__ void __launch_bounds__(256) emit_keys(int P, const float4* __restrict__ records,
-                                                const float* __restrict__ depths, const int* __restrict__ radii,
-                                                const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
-                                                uint32_t* __restrict__ values, int grid_x, int grid_y) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int r = radii[idx];
-    if (r <= 0) return;
-    uint32_t off = idx == 0 ? 0u : offsets[idx - 1];
-    const float4 a = records[(size_t)idx * B3_REC_VEC4];
-    int x0, y0, x1, y1;
-    tile_rect(a.x, a.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-    const uint64_t dbits = __float_as_uint(depths[idx]);
-    for (int y = y0; y < y1; y++) {
-        for (int x = x0; x < x1; x++) {
-            uint64_t key = (uint64_t)(uint32_t)(y * grid_x + x);
-            key = (key << 32) | dbits;
-            keys[off] = key;
-            values[off] = (uint32_t)idx;
-            off++;
+// ------------------------------------------------------------------ radix pass (8-bit digits)
+constexpr int kRadixThreads = 256;
+constexpr int kRadixItems = 16;
+constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
+constexpr int kRadixBins = 256;
+
+static int radix_blocks(int n) { return (n + kRadixTile - 1) / kRadixTile; }
+
+// hist[d * nb + b] = number of keys of block b with digit d.
+__global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __restrict__ keys, int n, int shift,
+                                                           uint32_t* __restrict__ hist, int nb) {
+    __shared__ uint32_t s_cnt[kRadixBins];
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kRadixTile;
+#pragma unroll
+    for (int i = 0; i < kRadixItems; i++) {
+        const int j = base + i * kRadixThreads + threadIdx.x;
+        if (j < n) atomicAdd(&s_cnt[(keys[j] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// One block per digit: exclusive scan of the digit's row over blocks, row total out.
+__global__ void __launch_bounds__(256) radix_rowscan(uint32_t* __restrict__ hist, int nb,
+                                                    uint32_t* __restrict__ digit_totals) {
+    __shared__ uint32_t s_warp[32];
+    uint32_t* row = hist + (size_t)blockIdx.x * nb;
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += 256) {
+        const int j = base + threadIdx.x;
+        const uint32_t v = j < nb ? row[j] : 0;
+        uint32_t total;
+        const uint32_t inc = block_inclusive_scan(v, s_warp, total);
+        if (j < nb) row[j] = carry + inc - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) digit_totals[blockIdx.x] = carry;
+}
+
+// Stable rank-and-scatter of one 4096-key tile.  kIota: values are the key indices.
+template <bool kIota>
+__global__ void __launch_bounds__(kRadixThreads) radix_scatter(const uint32_t* __restrict__ keys_in,
+                                                              const uint32_t* __restrict__ vals_in,
+                                                              uint32_t* __restrict__ keys_out,
+                                                              uint32_t* __restrict__ vals_out,
+                                                              const uint32_t* __restrict__ hist_scanned,
+                                                              const uint32_t* __restrict__ digit_totals, int n,
+                                                              int shift, int nb) {
+    __shared__ uint32_t s_warp_cnt[kRadixThreads / 32][kRadixBins];  // 8 KB
+    __shared__ uint32_t s_global_base[kRadixBins];
+    __shared__ uint32_t s_block_start[kRadixBins];
+    __shared__ uint32_t s_scan[32];
+    __shared__ uint32_t s_keys[kRadixTile];  // 16 KB
+    __shared__ uint32_t s_vals[kRadixTile];  // 16 KB
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int base = blockIdx.x * kRadixTile;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+#pragma unroll
+    for (int w = 0; w < kRadixThreads / 32; w++) s_warp_cnt[w][tid] = 0;
+    {
+        // global base of digit `tid` = (keys with a smaller digit) + (same digit, earlier blocks)
+        const uint32_t tot = digit_totals[tid];
+        uint32_t all;
+        const uint32_t inc = block_inclusive_scan(tot, s_scan, all);
+        s_global_base[tid] = inc - tot + hist_scanned[(size_t)tid * nb + blockIdx.x];
+    }
+    __syncthreads();
+
+    uint32_t k[kRadixItems], v[kRadixItems];
+    uint32_t rank[kRadixItems];
+#pragma unroll
+    for (int r = 0; r < kRadixItems; r++) {
+        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
+        const bool valid = j < n;
+        k[r] = valid ? keys_in[j] : 0xffffffffu;
+        v[r] = valid ? (kIota ? (uint32_t)j : vals_in[j]) : 0u;
+        // out-of-range slots sit at the very end of the tile and carry digit 255, so they
+        // rank after every real key and are simply not written back.
+        const uint32_t d = valid ? ((k[r] >> shift) & 0xffu) : 0xffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t cnt = s_warp_cnt[warp][d];
+        __syncwarp();
+        rank[r] = cnt + __popc(peers & lt_mask);
+        if ((peers & lt_mask) == 0) s_warp_cnt[warp][d] = cnt + __popc(peers);  // lowest peer updates
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        // digit `tid`: exclusive prefix over warps, block total, then prefix over digits
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kRadixThreads / 32; w++) {
+            const uint32_t c = s_warp_cnt[w][tid];
+            s_warp_cnt[w][tid] = run;
+            run += c;
+        }
+        uint32_t all;
+        const uint32_t inc = block_inclusive_scan(run, s_scan, all);
+        s_block_start[tid] = inc - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRadixItems; r++) {
+        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;
+        const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
+        const uint32_t pos = s_block_start[d] + s_warp_cnt[warp][d] + rank[r];
+        s_keys[pos] = k[r];
+        s_vals[pos] = v[r];
+    }
+    __syncthreads();
+    const int nvalid = min(kRadixTile, n - base);
+    for (int i = tid; i < nvalid; i += kRadixThreads) {
+        const uint32_t key = s_keys[i];
+        const uint32_t d = (key >> shift) & 0xffu;
+        const uint32_t g = s_global_base[d] + ((uint32_t)i - s_block_start[d]);
+        keys_out[g] = key;
+        vals_out[g] = s_vals[i];
+    }
+}
+
+// One stable 8-bit pass.  scratch: hist u32[256*nb] + digit_totals u32[256].
+static void radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       uint32_t* hist, uint32_t* digit_totals, int n, int shift, bool iota, cudaStream_t stream) {
+    const int nb = radix_blocks(n);
+    radix_hist<<<nb, kRadixThreads, 0, stream>>>(keys_in, n, shift, hist, nb);
+    radix_rowscan<<<kRadixBins, 256, 0, stream>>>(hist, nb, digit_totals);
+    if (iota)
+        radix_scatter<true><<<nb, kRadixThreads, 0, stream>>>(keys_in, nullptr, keys_out, vals_out, hist, digit_totals,
+                                                            n, shift, nb);
+    else
+        radix_scatter<false><<<nb, kRadixThreads, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, hist,
+                                                             digit_totals, n, shift, nb);
+    count_launch(3);
+}
+
+static size_t radix_scratch_elems(int n) { return (size_t)kRadixBins * radix_blocks(n) + kRadixBins; }
+
+// ------------------------------------------------------------------ phase 1 (P-sized)
+// scratch layout (u32 elements): keysA[P] keysB[P] valsA[P] valsB[P] hist[...] scan_sums[...]
+size_t binning_phase1_scratch_bytes(int P) {
+    const size_t p = (size_t)(P > 0 ? P : 0);
+    return (align_up(p * 4, 256) * 4 + align_up(radix_scratch_elems(P) * 4, 256) +
+            align_up((scan_tiles(P) + 1) * 4, 256));
+}
+
+cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) {
+    const size_t p = (size_t)a.P;
+    char* q = a.scratch;
+    uint32_t* keysB = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
+    uint32_t* keysC = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
+    uint32_t* valsA = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
+    uint32_t* valsB = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(q);  q += align_up(radix_scratch_elems(a.P) * 4, 256);
+    uint32_t* sums = reinterpret_cast<uint32_t*>(q);
+    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.P);
+    const uint32_t* dkeys = reinterpret_cast<const uint32_t*>(a.depths);
+    // 4 stable passes over float_bits(depth); depth > 0.2 for every visible Gaussian so
+    // unsigned order == float order, and the reference sorts the raw bits anyway.
+    radix_pass(dkeys, nullptr, keysB, valsA, hist, totals, a.P, 0, true, stream);
+    radix_pass(keysB, valsA, keysC, valsB, hist, totals, a.P, 8, false, stream);
+    radix_pass(keysC, valsB, keysB, valsA, hist, totals, a.P, 16, false, stream);
+    radix_pass(keysB, valsA, keysC, a.sorted_ids, hist, totals, a.P, 24, false, stream);
+    // emission offsets in depth order
+    exclusive_scan_gather(a.tiles_touched, a.sorted_ids, a.sorted_offsets, sums, nullptr, a.P, stream);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ phase 2 (R-sized)
+// One warp per 32 depth-ordered Gaussians; the lanes cooperatively write each Gaussian's
+// rectangle of tile ids (coalesced runs), so a Gaussian covering 2000 tiles costs its
+// warp 63 iterations instead of one thread 2000.
+__global__ void __launch_bounds__(256) emit_instances(int P, const uint32_t* __restrict__ sorted_ids,
+                                                     const uint32_t* __restrict__ sorted_offsets,
+                                                     const float4* __restrict__ records, const int* __restrict__ radii,
+                                                     uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ ids,
+                                                     int grid_x, int grid_y) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t g = 0, off = 0;
+    int x0 = 0, y0 = 0, w = 0, cnt = 0;
+    if (i < P) {
+        g = sorted_ids[i];
+        const int r = radii[g];
+        if (r > 0) {
+            const float4 a = records[(size_t)g * B3_REC_VEC4];
+            int x1, y1;
+            tile_rect(a.x, a.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
+            w = x1 - x0;
+            cnt = w * (y1 - y0);
+            off = sorted_offsets[i];
+        }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t sg = __shfl_sync(0xffffffffu, g, src);
+        const uint32_t soff = __shfl_sync(0xffffffffu, off, src);
+        const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+        const int sw = __shfl_sync(0xffffffffu, w, src), scnt = __shfl_sync(0xffffffffu, cnt, src);
+        for (int t = lane; t < scnt; t += 32) {
+            const int ty = t / sw, tx = t - ty * sw;
+            tile_keys[soff + t] = (uint32_t)((sy0 + ty) * grid_x + sx0 + tx);
+            ids[soff + t] = sg;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) tile_ranges(int R, const uint64_t* __restrict__ keys,
-                                                  uint2* __restrict__ ranges) {
+__global__ void __launch_bounds__(256) tile_ranges_u32(int R, const uint32_t* __restrict__ tile_keys,
+                                                      uint2* __restrict__ ranges) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    const uint32_t cur = tile_keys[idx];
     if (idx == 0) {
         ranges[cur].x = 0;
     } else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        const uint32_t prev = tile_keys[idx - 1];
         if (cur != prev) {
             ranges[prev].y = idx;
             ranges[cur].x = idx;
@@ -158,10 +366,50 @@ __global__ void __launch_bounds__(256) tile_ranges(int R, const uint64_t* __rest
     if (idx == R - 1) ranges[cur].y = R;
 }
 
-// rasterizer_impl.cu:35-50
-static uint32_t higher_msb(uint32_t n) {
-    uint32_t msb = sizeof(n) * 4;
-    uint32_t step = msb;
+static int tile_passes(int T) {
+    int bits = 0;
+    while ((1ll << bits) < (long long)T) bits++;
+    return bits <= 8 ? 1 : (bits <= 16 ? 2 : (bits <= 24 ? 3 : 4));
+}
+
+// ---- legacy cub path (A/B only)
+__global__ void __launch_bounds__(256) emit_keys64(int P, const float4* __restrict__ records,
+                                                  const float* __restrict__ depths, const int* __restrict__ radii,
+                                                  const uint32_t* __restrict__ sorted_ids,
+                                                  const uint32_t* __restrict__ sorted_offsets,
+                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x,
+                                                  int grid_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint32_t idx = sorted_ids[i];
+    const int r = radii[idx];
+    if (r <= 0) return;
+    uint32_t off = sorted_offsets[i];
+    const float4 a = records[(size_t)idx * B3_REC_VEC4];
+    int x0, y0, x1, y1;
+    tile_rect(a.x, a.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
+    const uint64_t dbits = __float_as_uint(depths[idx]);
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            keys[off] = ((uint64_t)(uint32_t)(y * grid_x + x) << 32) | dbits;
+            values[off] = idx;
+            off++;
+        }
+}
+__global__ void __launch_bounds__(256) tile_ranges_u64(int R, const uint64_t* __restrict__ keys,
+                                                      uint2* __restrict__ ranges) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R) return;
+    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+    }
+    if (idx == R - 1) ranges[cur].y = R;
+}
+static uint32_t higher_msb(uint32_t n) {  // rasterizer_impl.cu:35-50
+    uint32_t msb = sizeof(n) * 4, step = msb;
     while (step > 1) {
         step /= 2;
         if (n >> msb) msb += step; else msb -= step;
@@ -169,44 +417,72 @@ static uint32_t higher_msb(uint32_t n) {
     if (n >> msb) msb++;
     return msb;
 }
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
 static size_t cub_sort_temp_bytes(int R) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, R);
     return bytes;
 }
-
-size_t binning_scratch_bytes(int R) {
-    // keys_unsorted u64[R] | keys_sorted u64[R] | values_unsorted u32[R] | cub temp
-    size_t r = (size_t)(R > 0 ? R : 0);
-    return align_up(r * 8, 256) * 2 + align_up(r * 4, 256) + align_up(cub_sort_temp_bytes(R), 256) + 256;
+static bool use_cub() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B3GS_BINNING");
+        v = (e && !strcmp(e, "cub")) ? 1 : 0;
+    }
+    return v == 1;
 }
 
-cudaError_t run_binning(const BinningArgs& a, cudaStream_t stream) {
+size_t binning_phase2_scratch_bytes(int R) {
+    const size_t r = (size_t)(R > 0 ? R : 0);
+    if (use_cub())
+        return align_up(r * 8, 256) * 2 + align_up(r * 4, 256) + align_up(cub_sort_temp_bytes(R), 256) + 256;
+    // keysA[R] keysB[R] idsB[R] hist
+    return align_up(r * 4, 256) * 3 + align_up(radix_scratch_elems(R) * 4, 256);
+}
+
+cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream) {
     const int T = a.grid_x * a.grid_y;
     cudaError_t e = cudaMemsetAsync(a.ranges, 0, (size_t)T * sizeof(uint2), stream);
     if (e != cudaSuccess) return e;
     if (a.R <= 0) return cudaSuccess;
     const size_t r = (size_t)a.R;
-    char* p = a.scratch;
-    uint64_t* keys_unsorted = reinterpret_cast<uint64_t*>(p); p += align_up(r * 8, 256);
-    uint64_t* keys_sorted = reinterpret_cast<uint64_t*>(p);   p += align_up(r * 8, 256);
-    uint32_t* values_unsorted = reinterpret_cast<uint32_t*>(p); p += align_up(r * 4, 256);
-    size_t temp_bytes = cub_sort_temp_bytes(a.R);
-    void* temp = p;
-
-    emit_keys<<<(a.P + 255) / 256, 256, 0, stream>>>(a.P, a.records, a.depths, a.radii, a.point_offsets,
-                                                    keys_unsorted, values_unsorted, a.grid_x, a.grid_y);
+    char* q = a.scratch;
+    if (use_cub()) {
+        uint64_t* keys_unsorted = reinterpret_cast<uint64_t*>(q); q += align_up(r * 8, 256);
+        uint64_t* keys_sorted = reinterpret_cast<uint64_t*>(q);   q += align_up(r * 8, 256);
+        uint32_t* values_unsorted = reinterpret_cast<uint32_t*>(q); q += align_up(r * 4, 256);
+        size_t temp_bytes = cub_sort_temp_bytes(a.R);
+        emit_keys64<<<(a.P + 255) / 256, 256, 0, stream>>>(a.P, a.records, a.depths, a.radii, a.sorted_ids,
+                                                          a.sorted_offsets, keys_unsorted, values_unsorted, a.grid_x,
+                                                          a.grid_y);
+        e = cub::DeviceRadixSort::SortPairs(q, temp_bytes, keys_unsorted, keys_sorted, values_unsorted, a.point_list,
+                                            a.R, 0, 32 + (int)higher_msb((uint32_t)T), stream);
+        if (e != cudaSuccess) return e;
+        tile_ranges_u64<<<(a.R + 255) / 256, 256, 0, stream>>>(a.R, keys_sorted, a.ranges);
+        count_launch(10);
+        return cudaGetLastError();
+    }
+    uint32_t* keysA = reinterpret_cast<uint32_t*>(q); q += align_up(r * 4, 256);
+    uint32_t* keysB = reinterpret_cast<uint32_t*>(q); q += align_up(r * 4, 256);
+    uint32_t* idsB = reinterpret_cast<uint32_t*>(q);  q += align_up(r * 4, 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(q);
+    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.R);
+    // ping-pong so that the LAST pass writes the ids into point_list
+    const int passes = tile_passes(T);
+    uint32_t* ids_cur = (passes & 1) ? idsB : a.point_list;  // where emission writes
+    uint32_t* ids_oth = (passes & 1) ? a.point_list : idsB;
+    uint32_t* keys_cur = keysA;
+    uint32_t* keys_oth = keysB;
+    emit_instances<<<(a.P + 255) / 256, 256, 0, stream>>>(a.P, a.sorted_ids, a.sorted_offsets, a.records, a.radii,
+                                                         keys_cur, ids_cur, a.grid_x, a.grid_y);
     count_launch();
-    const int bit = (int)higher_msb((uint32_t)T);
-    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_unsorted, keys_sorted, values_unsorted,
-                                        a.point_list, a.R, 0, 32 + bit, stream);
-    if (e != cudaSuccess) return e;
-    count_launch(8);  // histogram + onesweep passes (library kernels)
-    tile_ranges<<<(a.R + 255) / 256, 256, 0, stream>>>(a.R, keys_sorted, a.ranges);
+    for (int p = 0; p < passes; p++) {
+        radix_pass(keys_cur, ids_cur, keys_oth, ids_oth, hist, totals, a.R, 8 * p, false, stream);
+        uint32_t* t = keys_cur; keys_cur = keys_oth; keys_oth = t;
+        t = ids_cur; ids_cur = ids_oth; ids_oth = t;
+    }
+    // ids_cur == a.point_list by construction
+    tile_ranges_u32<<<(a.R + 255) / 256, 256, 0, stream>>>(a.R, keys_cur, a.ranges);
     count_launch();
     return cudaGetLastError();
 }

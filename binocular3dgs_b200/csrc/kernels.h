@@ -31,31 +31,40 @@ struct PreprocessArgs {
     float* depths;
     uint32_t* tiles_touched;
     uint8_t* clamped;
+    uint32_t* num_rendered;  // device counter, zeroed by the caller; += sum(tiles_touched)
 };
 void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                          cudaStream_t stream);
 
 // ---------------------------------------------------------------- binning (K2-K5)
-// Inclusive prefix sum of tiles_touched -> point_offsets (u32), P elements.
-// `block_sums` is scratch of scan_scratch_elems(P) u32.
-size_t scan_scratch_elems(int P);
-void launch_inclusive_scan(const uint32_t* in, uint32_t* out, uint32_t* block_sums, int P, cudaStream_t stream);
+// Phase 1 needs only P-sized state and is enqueued BEFORE the host reads R, so the GPU
+// sorts by depth while the host waits for the count and allocates the R-sized blob.
+struct BinningPhase1Args {
+    int P;
+    const float* depths;            // sort key: float bits
+    const uint32_t* tiles_touched;
+    uint32_t* sorted_ids;           // out: Gaussian ids in (depth bits, id) order, P
+    uint32_t* sorted_offsets;       // out: exclusive scan of tiles_touched in that order, P
+    char* scratch;
+};
+size_t binning_phase1_scratch_bytes(int P);
+cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream);
 
-struct BinningArgs {
+struct BinningPhase2Args {
     int P, R;
     int grid_x, grid_y;
     const float4* records;
     const float* depths;
     const int* radii;
-    const uint32_t* point_offsets;  // inclusive scan of tiles_touched
+    const uint32_t* sorted_ids;
+    const uint32_t* sorted_offsets;
     uint32_t* point_list;           // out: sorted Gaussian ids, R
     uint2* ranges;                  // out: per-tile [start,end), T
-    char* scratch;                  // binning scratch (after point_list in the blob)
-    size_t scratch_bytes;
+    char* scratch;
 };
-size_t binning_scratch_bytes(int R);
-cudaError_t run_binning(const BinningArgs& a, cudaStream_t stream);
+size_t binning_phase2_scratch_bytes(int R);
+cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- K6 / K7
 struct CompositeFwdArgs {

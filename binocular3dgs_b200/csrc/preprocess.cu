@@ -43,6 +43,7 @@ struct PreParams {
     float* depths;
     uint32_t* tiles_touched;
     uint8_t* clamped;
+    uint32_t* num_rendered;
 };
 
 // SH -> RGB, forward.cu:20-71.  dir components are IEEE divisions by the IEEE
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
     }
     __syncthreads();
     const int t = threadIdx.x;
-    if (t >= n) return;
-    const int idx = base + t;
+    const bool in_range = t < n;
+    const int idx = base + (in_range ? t : 0);
 
     const float x = s_mean[3 * t], y = s_mean[3 * t + 1], z = s_mean[3 * t + 2];
     const float* __restrict__ V = p.viewmatrix;
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
 
     // in_frustum (auxiliary.h:139-164): only the view-space z is live.
     const float pz = xform(V[2], V[6], V[10], V[14], x, y, z);
-    bool alive = !(pz <= 0.2f);
-    if (!alive && p.prefiltered) {
+    bool alive = in_range && !(pz <= 0.2f);
+    if (in_range && !alive && p.prefiltered) {
         printf("Point is filtered although prefiltered is set. This shouldn't happen!");
         __trap();
     }
@@ -268,12 +269,23 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
             }
         }
     }
-    p.radii[idx] = radius_out;
-    p.tiles_touched[idx] = tiles;
-    p.depths[idx] = depth;
-    p.clamped[idx] = clamp_bits;
-    float4* rec = p.records + (size_t)idx * B3_REC_VEC4;
-    rec[0] = ra; rec[1] = rb; rec[2] = rc;
+    if (in_range) {
+        p.radii[idx] = radius_out;
+        p.tiles_touched[idx] = tiles;
+        p.depths[idx] = depth;
+        p.clamped[idx] = clamp_bits;
+        float4* rec = p.records + (size_t)idx * B3_REC_VEC4;
+        rec[0] = ra; rec[1] = rb; rec[2] = rc;
+    }
+    // R = sum(tiles_touched): warp shuffle reduce, one shared atomic per warp, one global
+    // atomic per block — replaces the reference's full prefix sum + read of its last element.
+    __shared__ uint32_t s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_total, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(p.num_rendered, s_total);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ V,
@@ -296,7 +308,7 @@ void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream) {
     p.focal_x = a.focal_x; p.focal_y = a.focal_y;
     p.grid_x = a.grid_x; p.grid_y = a.grid_y; p.prefiltered = a.prefiltered;
     p.radii = a.radii; p.records = a.records; p.depths = a.depths;
-    p.tiles_touched = a.tiles_touched; p.clamped = a.clamped;
+    p.tiles_touched = a.tiles_touched; p.clamped = a.clamped; p.num_rendered = a.num_rendered;
     preprocess_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(p);
     count_launch();
 }
