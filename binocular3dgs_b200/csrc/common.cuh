@@ -18,8 +18,8 @@
 
 // Per-Gaussian record written by the preprocess and gathered by both composite
 // kernels: three 16-byte vectors, 48 B, so one Gaussian is three LDG.128.
-//   a = { x, y, ext_x, ext_y }   pixel-space mean and the conservative half-extents
-//                                of the region where alpha can reach 1/255
+//   a = { x, y, tau, 0 }         pixel-space mean and the conservative culling threshold:
+//                                alpha can reach 1/255 only where q(d) <= tau
 //   b = { conic.x, conic.y, conic.z, opacity }
 //   c = { r, g, b, depth }
 #define B3_REC_VEC4 3

@@ -92,27 +92,25 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
     r = c0; g = c1; b = c2;
 }
 
-// Conservative half-extents (pixels) of the set where this Gaussian's alpha can
-// reach 1/255: { d : 0.5*(cx dx^2 + cz dy^2) + cy dx dy <= tau }, tau = ln(255*o).
-// This is NOT in the reference; it only lets a warp skip list entries that cannot
-// touch its pixels.  It must never exclude a pixel the exact per-pixel test
-// (power <= 0 && o*exp(power) >= 1/255) would accept, hence the inflated tau, the
-// added half-pixel-ish slack and the "give up" cases that disable culling.
-__device__ __forceinline__ void cull_extent(float px, float py, float cx, float cy, float cz, float o,
-                                            float& ex, float& ey) {
-    const float kHuge = 3.0e38f;
-    ex = kHuge; ey = kHuge;
-    if (!(o >= 0.0f)) return;               // NaN / negative opacity: no culling
-    if (o < 0.0039f) { ex = -1.0f; ey = -1.0f; return; }  // o*G < 1/255 for every G <= 1
-    float det = cx * cz - cy * cy;
-    if (!(cx > 0.0f) || !(cz > 0.0f) || !(det > 1e-3f * cx * cz)) return;  // not safely PSD
-    if (!(fabsf(px) < 1.0e5f) || !(fabsf(py) < 1.0e5f)) return;
-    float tau = 1.01f * logf(255.0f * o) + 0.05f;
-    float inv = 2.0f * tau / det;
-    float ex2 = inv * cz, ey2 = inv * cx;
-    if (!(ex2 < 1.0e10f) || !(ey2 < 1.0e10f)) return;
-    ex = sqrtf(ex2) * 1.0001f + 0.05f;
-    ey = sqrtf(ey2) * 1.0001f + 0.05f;
+// Conservative cut-off for culling: this Gaussian can reach alpha >= 1/255 at pixel
+// offset d only if  q(d) = 0.5*(cx dx^2 + cz dy^2) + cy dx dy <= tau,  tau = ln(255*o).
+// The composite kernels minimise q exactly over a warp's pixel rectangle and skip the
+// entry when the minimum exceeds the value returned here.  This is NOT in the
+// reference; it must never exclude a pixel the exact per-pixel test
+// (power <= 0 && o*exp(power) >= 1/255) would accept, hence tau is inflated (1 % + 0.05,
+// which dominates the float error of evaluating q for conics that are comfortably
+// positive definite) and culling is disabled (+huge) for anything unusual.
+//   returns  < 0     : can never contribute (o*G < 1/255 for every G <= 1)
+//            >= 3e38 : never cull
+__device__ __forceinline__ float cull_threshold(float px, float py, float cx, float cy, float cz, float o) {
+    const float kNever = 3.0e38f;
+    if (!(o >= 0.0f)) return kNever;          // NaN / negative opacity
+    if (o < 0.0039f) return -1.0f;            // 0.0039 < 1/255: o*G < 1/255 whenever G <= 1
+    const float det = cx * cz - cy * cy;
+    if (!(cx > 0.0f) || !(cz > 0.0f) || !(det > 1e-3f * cx * cz)) return kNever;  // not safely PSD
+    if (!(cx < 1.0e4f) || !(cz < 1.0e4f)) return kNever;
+    if (!(fabsf(px) < 1.0e5f) || !(fabsf(py) < 1.0e5f)) return kNever;
+    return 1.01f * logf(255.0f * o) + 0.05f;
 }
 
 __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
@@ -137,7 +135,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
     int radius_out = 0;
     uint32_t tiles = 0;
     float depth = 0.0f;
-    float4 ra = make_float4(0.f, 0.f, -1.f, -1.f), rb = make_float4(0.f, 0.f, 0.f, 0.f),
+    float4 ra = make_float4(0.f, 0.f, -1.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f),
            rc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint8_t clamp_bits = 0;
 
@@ -258,12 +256,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
                     cr = c[0]; cg = c[1]; cbl = c[2];
                 }
                 const float op = p.opacities[idx];
-                float ex, ey;
-                cull_extent(pix_x, pix_y, conx, cony, conz, op, ex, ey);
+                const float tau = cull_threshold(pix_x, pix_y, conx, cony, conz, op);
                 depth = pz;
                 radius_out = ri;
                 tiles = area;
-                ra = make_float4(pix_x, pix_y, ex, ey);
+                ra = make_float4(pix_x, pix_y, tau, 0.0f);
                 rb = make_float4(conx, cony, conz, op);
                 rc = make_float4(cr, cg, cbl, pz);
             }

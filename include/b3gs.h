@@ -188,7 +188,7 @@ B3GS_API size_t b3gs_image_bytes(int width, int height);
  * SURVEY.md §8c): byte offsets of named arrays inside the blobs.  Returns the
  * offset, or (size_t)-1 for an unknown name.
  *   geometry: "depths" f32[P], "tiles_touched" u32[P], "point_offsets" u32[P],
- *             "records" f32[P,12] = {x, y, ext_x, ext_y | conic_x, conic_y, conic_z,
+ *             "records" f32[P,12] = {x, y, cull_tau, 0 | conic_x, conic_y, conic_z,
  *             opacity | r, g, b, depth}, "clamped" u8[P] (bit c = channel c clamped)
  *   binning:  "point_list" u32[R]
  *   image:    "n_contrib" u32[H*W], "ranges" u32[T,2]
