@@ -317,7 +317,7 @@ def main():
 
     # ---------------- CPU baseline (oracle port), rank 0 only, bounded sample
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # N=1 only (torchrun pins OMP threads to 1)
         from oracle import cpu_oracle as orc
         a = [t.numpy() for t in scene_c.tensors()]
         gcn, gdn, gan = (t.cpu().numpy() for t in (gc, gd, ga))

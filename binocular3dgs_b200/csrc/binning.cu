@@ -150,13 +150,20 @@ static int radix_blocks(int n) { return (n + kRadixTile - 1) / kRadixTile; }
 __global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __restrict__ keys, int n, int shift,
                                                            uint32_t* __restrict__ hist, int nb) {
     __shared__ uint32_t s_cnt[kRadixBins];
-    s_cnt[threadIdx.x] = 0;
-    __syncthreads();
     const int base = blockIdx.x * kRadixTile;
+    // all 16 loads in flight before the first shared atomic (one memory round trip)
+    uint32_t k[kRadixItems];
 #pragma unroll
     for (int i = 0; i < kRadixItems; i++) {
         const int j = base + i * kRadixThreads + threadIdx.x;
-        if (j < n) atomicAdd(&s_cnt[(keys[j] >> shift) & 0xffu], 1u);
+        k[i] = j < n ? __ldg(keys + j) : 0u;
+    }
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRadixItems; i++) {
+        const int j = base + i * kRadixThreads + threadIdx.x;
+        if (j < n) atomicAdd(&s_cnt[(k[i] >> shift) & 0xffu], 1u);
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
@@ -198,6 +205,16 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter(const uint32_t* _
     const int base = blockIdx.x * kRadixTile;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    // issue every global load of the tile first (one memory round trip), then rank
+    uint32_t k[kRadixItems], v[kRadixItems];
+    uint32_t rank[kRadixItems];
+#pragma unroll
+    for (int r = 0; r < kRadixItems; r++) {
+        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
+        const bool valid = j < n;
+        k[r] = valid ? __ldg(keys_in + j) : 0xffffffffu;
+        v[r] = valid ? (kIota ? (uint32_t)j : __ldg(vals_in + j)) : 0u;
+    }
 #pragma unroll
     for (int w = 0; w < kRadixThreads / 32; w++) s_warp_cnt[w][tid] = 0;
     {
@@ -208,18 +225,12 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter(const uint32_t* _
         s_global_base[tid] = inc - tot + hist_scanned[(size_t)tid * nb + blockIdx.x];
     }
     __syncthreads();
-
-    uint32_t k[kRadixItems], v[kRadixItems];
-    uint32_t rank[kRadixItems];
 #pragma unroll
     for (int r = 0; r < kRadixItems; r++) {
-        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
-        const bool valid = j < n;
-        k[r] = valid ? keys_in[j] : 0xffffffffu;
-        v[r] = valid ? (kIota ? (uint32_t)j : vals_in[j]) : 0u;
+        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;
         // out-of-range slots sit at the very end of the tile and carry digit 255, so they
         // rank after every real key and are simply not written back.
-        const uint32_t d = valid ? ((k[r] >> shift) & 0xffu) : 0xffu;
+        const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const uint32_t cnt = s_warp_cnt[warp][d];
         __syncwarp();
