@@ -26,6 +26,7 @@
 // spin-waiting anywhere (three plain kernels per pass), so a bug cannot hang the GPU.
 //
 // The cub path the first revision used is kept behind B3GS_BINNING=cub for A/B timing.
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdlib>
@@ -33,6 +34,8 @@
 
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace b3 {
 
@@ -146,17 +149,33 @@ constexpr int kRadixBins = 256;
 
 static int radix_blocks(int n) { return (n + kRadixTile - 1) / kRadixTile; }
 
-// hist[d * nb + b] = number of keys of block b with digit d.
-__global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __restrict__ keys, int n, int shift,
-                                                           uint32_t* __restrict__ hist, int nb) {
-    __shared__ uint32_t s_cnt[kRadixBins];
-    const int base = blockIdx.x * kRadixTile;
+// Loads of data another block wrote earlier IN THE SAME (cooperative) kernel must not
+// use the non-coherent path; everything else may.
+template <bool kCoop>
+__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) {
+    return kCoop ? __ldcg(p) : __ldg(p);
+}
+
+struct RadixSmem {
+    uint32_t warp_cnt[kRadixThreads / 32][kRadixBins];  // 8 KB
+    uint32_t global_base[kRadixBins];
+    uint32_t block_start[kRadixBins];
+    uint32_t scan[32];
+    uint32_t keys[kRadixTile];  // 16 KB
+    uint32_t vals[kRadixTile];  // 16 KB
+};
+
+// hist[d * nb + tile] = number of keys of `tile` with digit d.  s_cnt: 256 words.
+template <bool kCoop>
+__device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const uint32_t* __restrict__ keys, int n,
+                                                int shift, uint32_t* __restrict__ hist, int nb) {
+    const int base = tile * kRadixTile;
     // all 16 loads in flight before the first shared atomic (one memory round trip)
     uint32_t k[kRadixItems];
 #pragma unroll
     for (int i = 0; i < kRadixItems; i++) {
         const int j = base + i * kRadixThreads + threadIdx.x;
-        k[i] = j < n ? __ldg(keys + j) : 0u;
+        k[i] = j < n ? ld_u32<kCoop>(keys + j) : 0u;
     }
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -166,7 +185,14 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __re
         if (j < n) atomicAdd(&s_cnt[(k[i] >> shift) & 0xffu], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
+    hist[(size_t)threadIdx.x * nb + tile] = s_cnt[threadIdx.x];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __restrict__ keys, int n, int shift,
+                                                           uint32_t* __restrict__ hist, int nb) {
+    __shared__ uint32_t s_cnt[kRadixBins];
+    radix_hist_tile<false>(s_cnt, blockIdx.x, keys, n, shift, hist, nb);
 }
 
 // One block per digit: exclusive scan of the digit's row over blocks, row total out.
@@ -200,22 +226,15 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
 }
 
 // Stable rank-and-scatter of one 4096-key tile.  kIota: values are the key indices.
-template <bool kIota>
-__global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t* __restrict__ keys_in,
-                                                              const uint32_t* __restrict__ vals_in,
-                                                              uint32_t* __restrict__ keys_out,
-                                                              uint32_t* __restrict__ vals_out,
-                                                              const uint32_t* __restrict__ hist_scanned,
-                                                              const uint32_t* __restrict__ digit_totals, int n,
-                                                              int shift, int nb) {
-    __shared__ uint32_t s_warp_cnt[kRadixThreads / 32][kRadixBins];  // 8 KB
-    __shared__ uint32_t s_global_base[kRadixBins];
-    __shared__ uint32_t s_block_start[kRadixBins];
-    __shared__ uint32_t s_scan[32];
-    __shared__ uint32_t s_keys[kRadixTile];  // 16 KB
-    __shared__ uint32_t s_vals[kRadixTile];  // 16 KB
+template <bool kIota, bool kCoop>
+__device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, const uint32_t* __restrict__ keys_in,
+                                                   const uint32_t* __restrict__ vals_in,
+                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                   const uint32_t* __restrict__ hist_scanned,
+                                                   const uint32_t* __restrict__ digit_totals, int n, int shift,
+                                                   int nb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int base = blockIdx.x * kRadixTile;
+    const int base = tile * kRadixTile;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // issue every global load of the tile first (one memory round trip), then rank
@@ -225,17 +244,17 @@ __global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t
     for (int r = 0; r < kRadixItems; r++) {
         const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
         const bool valid = j < n;
-        k[r] = valid ? __ldg(keys_in + j) : 0xffffffffu;
-        v[r] = valid ? (kIota ? (uint32_t)j : __ldg(vals_in + j)) : 0u;
+        k[r] = valid ? ld_u32<kCoop>(keys_in + j) : 0xffffffffu;
+        v[r] = valid ? (kIota ? (uint32_t)j : ld_u32<kCoop>(vals_in + j)) : 0u;
     }
 #pragma unroll
-    for (int w = 0; w < kRadixThreads / 32; w++) s_warp_cnt[w][tid] = 0;
+    for (int w = 0; w < kRadixThreads / 32; w++) sm.warp_cnt[w][tid] = 0;
     {
         // global base of digit `tid` = (keys with a smaller digit) + (same digit, earlier blocks)
-        const uint32_t tot = digit_totals[tid];
+        const uint32_t tot = ld_u32<kCoop>(digit_totals + tid);
         uint32_t all;
-        const uint32_t inc = block_inclusive_scan(tot, s_scan, all);
-        s_global_base[tid] = inc - tot + hist_scanned[(size_t)tid * nb + blockIdx.x];
+        const uint32_t inc = block_inclusive_scan(tot, sm.scan, all);
+        sm.global_base[tid] = inc - tot + ld_u32<kCoop>(hist_scanned + (size_t)tid * nb + tile);
     }
     __syncthreads();
 #pragma unroll
@@ -245,11 +264,11 @@ __global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t
         // rank after every real key and are simply not written back.
         const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
         const unsigned peers = match_digit8(d);
-        const uint32_t cnt = s_warp_cnt[warp][d];
+        const uint32_t cnt = sm.warp_cnt[warp][d];
         __syncwarp();
         const uint32_t rk = cnt + __popc(peers & lt_mask);
         if (r & 1) rank2[r >> 1] |= rk << 16; else rank2[r >> 1] = rk;
-        if ((peers & lt_mask) == 0) s_warp_cnt[warp][d] = cnt + __popc(peers);  // lowest peer updates
+        if ((peers & lt_mask) == 0) sm.warp_cnt[warp][d] = cnt + __popc(peers);  // lowest peer updates
         __syncwarp();
     }
     __syncthreads();
@@ -258,13 +277,13 @@ __global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kRadixThreads / 32; w++) {
-            const uint32_t c = s_warp_cnt[w][tid];
-            s_warp_cnt[w][tid] = run;
+            const uint32_t c = sm.warp_cnt[w][tid];
+            sm.warp_cnt[w][tid] = run;
             run += c;
         }
         uint32_t all;
-        const uint32_t inc = block_inclusive_scan(run, s_scan, all);
-        s_block_start[tid] = inc - run;
+        const uint32_t inc = block_inclusive_scan(run, sm.scan, all);
+        sm.block_start[tid] = inc - run;
     }
     __syncthreads();
 #pragma unroll
@@ -272,19 +291,33 @@ __global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t
         const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;
         const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
         const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
-        const uint32_t pos = s_block_start[d] + s_warp_cnt[warp][d] + rk;
-        s_keys[pos] = k[r];
-        s_vals[pos] = v[r];
+        const uint32_t pos = sm.block_start[d] + sm.warp_cnt[warp][d] + rk;
+        sm.keys[pos] = k[r];
+        sm.vals[pos] = v[r];
     }
     __syncthreads();
     const int nvalid = min(kRadixTile, n - base);
     for (int i = tid; i < nvalid; i += kRadixThreads) {
-        const uint32_t key = s_keys[i];
+        const uint32_t key = sm.keys[i];
         const uint32_t d = (key >> shift) & 0xffu;
-        const uint32_t g = s_global_base[d] + ((uint32_t)i - s_block_start[d]);
+        const uint32_t g = sm.global_base[d] + ((uint32_t)i - sm.block_start[d]);
         keys_out[g] = key;
-        vals_out[g] = s_vals[i];
+        vals_out[g] = sm.vals[i];
     }
+    __syncthreads();
+}
+
+template <bool kIota>
+__global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t* __restrict__ keys_in,
+                                                              const uint32_t* __restrict__ vals_in,
+                                                              uint32_t* __restrict__ keys_out,
+                                                              uint32_t* __restrict__ vals_out,
+                                                              const uint32_t* __restrict__ hist_scanned,
+                                                              const uint32_t* __restrict__ digit_totals, int n,
+                                                              int shift, int nb) {
+    __shared__ RadixSmem sm;
+    radix_scatter_tile<kIota, false>(sm, blockIdx.x, keys_in, vals_in, keys_out, vals_out, hist_scanned, digit_totals,
+                                     n, shift, nb);
 }
 
 // One stable 8-bit pass.  scratch: hist u32[256*nb] + digit_totals u32[256].
@@ -305,11 +338,130 @@ static void radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_
 static size_t radix_scratch_elems(int n) { return (size_t)kRadixBins * radix_blocks(n) + kRadixBins; }
 
 // ------------------------------------------------------------------ phase 1 (P-sized)
+// The whole of phase 1 — four radix passes over float_bits(depth) and the gather-scan of
+// tiles_touched in the resulting order — as ONE cooperative kernel: the P-sized passes
+// are latency-bound (49 tiles at 200k Gaussians), so 15 separate launches cost more in
+// launch/drain latency than in work.  Grid-wide barriers replace the launch boundaries;
+// a cooperative launch either guarantees co-residency of all blocks or fails, it cannot
+// hang.  Falls back to the multi-kernel path when cooperative launch is unavailable.
+struct Phase1Args {
+    int P;
+    const uint32_t* dkeys;
+    const uint32_t* tiles_touched;
+    uint32_t *keysB, *keysC, *valsA, *valsB, *hist, *totals, *sums;
+    uint32_t *sorted_ids, *sorted_offsets;
+};
+
+__global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a) {
+    __shared__ RadixSmem sm;
+    cg::grid_group grid = cg::this_grid();
+    const int n = a.P;
+    const int nb = (n + kRadixTile - 1) / kRadixTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 8 * pass;
+        // ping-pong: keys dkeys->B->C->B->C, values iota->A->B->A->sorted_ids
+        const uint32_t* kin = pass == 0 ? a.dkeys : ((pass & 1) ? a.keysB : a.keysC);
+        uint32_t* kout = (pass & 1) ? a.keysC : a.keysB;
+        const uint32_t* vin = (pass & 1) ? a.valsA : a.valsB;
+        uint32_t* vout = pass == 3 ? a.sorted_ids : ((pass & 1) ? a.valsB : a.valsA);
+        for (int t = blockIdx.x; t < nb; t += gridDim.x)
+            radix_hist_tile<true>(sm.global_base, t, kin, n, shift, a.hist, nb);
+        grid.sync();
+        // row scan: one warp per digit row
+        for (int row = blockIdx.x * (kRadixThreads / 32) + warp; row < kRadixBins; row += gridDim.x * (kRadixThreads / 32)) {
+            uint32_t* r = a.hist + (size_t)row * nb;
+            uint32_t carry = 0;
+            for (int base = 0; base < nb; base += 32) {
+                const int j = base + lane;
+                const uint32_t v = j < nb ? __ldcg(r + j) : 0u;
+                const uint32_t inc = warp_inclusive_scan(v, lane);
+                if (j < nb) r[j] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) a.totals[row] = carry;
+        }
+        grid.sync();
+        for (int t = blockIdx.x; t < nb; t += gridDim.x) {
+            if (pass == 0)
+                radix_scatter_tile<true, true>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
+            else
+                radix_scatter_tile<false, true>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
+        }
+        grid.sync();
+    }
+    // exclusive scan of tiles_touched in depth order -> emission offsets
+    const int nt = (n + kScanTile - 1) / kScanTile;
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const int base = t * kScanTile;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            const int j = base + i * kScanThreads + threadIdx.x;
+            if (j < n) acc += __ldg(a.tiles_touched + __ldcg(a.sorted_ids + j));
+        }
+        uint32_t total;
+        block_inclusive_scan(acc, sm.scan, total);
+        if (threadIdx.x == 0) a.sums[t] = total;
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+        uint32_t carry = 0;
+        for (int base = 0; base < nt; base += kRadixThreads) {
+            const int j = base + threadIdx.x;
+            const uint32_t v = j < nt ? __ldcg(a.sums + j) : 0u;
+            uint32_t total;
+            const uint32_t inc = block_inclusive_scan(v, sm.scan, total);
+            if (j < nt) a.sums[j] = carry + inc - v;
+            carry += total;
+        }
+    }
+    grid.sync();
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const int base = t * kScanTile + threadIdx.x * kScanItems;  // blocked arrangement
+        uint32_t v[kScanItems];
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            v[i] = (base + i < n) ? __ldg(a.tiles_touched + __ldcg(a.sorted_ids + base + i)) : 0u;
+            acc += v[i];
+        }
+        uint32_t total;
+        const uint32_t inc = block_inclusive_scan(acc, sm.scan, total);
+        uint32_t run = __ldcg(a.sums + t) + inc - acc;
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            if (base + i < n) a.sorted_offsets[base + i] = run;
+            run += v[i];
+        }
+    }
+}
+
 // scratch layout (u32 elements): keysA[P] keysB[P] valsA[P] valsB[P] hist[...] scan_sums[...]
 size_t binning_phase1_scratch_bytes(int P) {
     const size_t p = (size_t)(P > 0 ? P : 0);
     return (align_up(p * 4, 256) * 4 + align_up(radix_scratch_elems(P) * 4, 256) +
             align_up((scan_tiles(P) + 1) * 4, 256));
+}
+
+// Largest cooperative grid for depth_sort_coop on the current device, 0 if unsupported.
+static int coop_grid_limit() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev == cached_dev) return cached;
+    cached_dev = dev;
+    cached = 0;
+    const char* e = getenv("B3GS_PHASE1");
+    if (e && !strcmp(e, "multi")) return 0;
+    int coop = 0, sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_sort_coop, kRadixThreads, 0) != cudaSuccess)
+        return 0;
+    cached = sms * per_sm;
+    return cached;
 }
 
 cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) {
@@ -323,6 +475,25 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
     uint32_t* sums = reinterpret_cast<uint32_t*>(q);
     uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.P);
     const uint32_t* dkeys = reinterpret_cast<const uint32_t*>(a.depths);
+    const int limit = coop_grid_limit();
+    if (limit > 0) {
+        Phase1Args k;
+        k.P = a.P; k.dkeys = dkeys; k.tiles_touched = a.tiles_touched;
+        k.keysB = keysB; k.keysC = keysC; k.valsA = valsA; k.valsB = valsB;
+        k.hist = hist; k.totals = totals; k.sums = sums;
+        k.sorted_ids = a.sorted_ids; k.sorted_offsets = a.sorted_offsets;
+        // at least 32 blocks so that the 256 digit rows find 256 warps
+        int grid = radix_blocks(a.P) < 32 ? 32 : radix_blocks(a.P);
+        if (grid > limit) grid = limit;
+        void* args[] = {&k};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)depth_sort_coop, dim3(grid), dim3(kRadixThreads), args,
+                                                    0, stream);
+        if (e == cudaSuccess) {
+            count_launch();
+            return cudaSuccess;
+        }
+        (void)cudaGetLastError();  // clear and fall through to the multi-kernel path
+    }
     // 4 stable passes over float_bits(depth); depth > 0.2 for every visible Gaussian so
     // unsigned order == float order, and the reference sorts the raw bits anyway.
     radix_pass(dkeys, nullptr, keysB, valsA, hist, totals, a.P, 0, true, stream);
