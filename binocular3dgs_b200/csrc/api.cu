@@ -219,7 +219,9 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         pa.tiles_touched = reinterpret_cast<uint32_t*>(geo + gl.tiles_touched);
         pa.clamped = reinterpret_cast<uint8_t*>(geo + gl.clamped);
         pa.num_rendered = reinterpret_cast<uint32_t*>(geo + gl.counter);
-        cudaError_t e = cudaMemsetAsync(pa.num_rendered, 0, sizeof(uint32_t), st);
+        // counter words: [0] R = 0, [1] OR of depth keys = 0, [2] AND of depth keys = ~0
+        cudaError_t e = cudaMemsetAsync(pa.num_rendered, 0, 2 * sizeof(uint32_t), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(pa.num_rendered + 2, 0xff, sizeof(uint32_t), st);
         if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "zero instance counter", e);
         {
             StageTimer t_(ST_PREPROCESS, st);
@@ -241,6 +243,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         {
             BinningPhase1Args b1;
             b1.P = P; b1.depths = pa.depths; b1.tiles_touched = pa.tiles_touched;
+            b1.key_bits = pa.num_rendered + 1;
             b1.sorted_ids = reinterpret_cast<uint32_t*>(geo + gl.sorted_ids);
             b1.sorted_offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
             b1.scratch = geo + gl.scratch;

@@ -226,7 +226,9 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
 }
 
 // Stable rank-and-scatter of one 4096-key tile.  kIota: values are the key indices.
-template <bool kIota, bool kCoop>
+// kPreloaded: the caller already put the digit totals in sm.block_start[] and the
+// same-digit-earlier-tiles prefix in sm.global_base[] (cooperative in-block-prefix path).
+template <bool kIota, bool kCoop, bool kPreloaded>
 __device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, const uint32_t* __restrict__ keys_in,
                                                    const uint32_t* __restrict__ vals_in,
                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -251,10 +253,11 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, cons
     for (int w = 0; w < kRadixThreads / 32; w++) sm.warp_cnt[w][tid] = 0;
     {
         // global base of digit `tid` = (keys with a smaller digit) + (same digit, earlier blocks)
-        const uint32_t tot = ld_u32<kCoop>(digit_totals + tid);
+        const uint32_t tot = kPreloaded ? sm.block_start[tid] : ld_u32<kCoop>(digit_totals + tid);
+        const uint32_t before = kPreloaded ? sm.global_base[tid] : ld_u32<kCoop>(hist_scanned + (size_t)tid * nb + tile);
         uint32_t all;
         const uint32_t inc = block_inclusive_scan(tot, sm.scan, all);
-        sm.global_base[tid] = inc - tot + ld_u32<kCoop>(hist_scanned + (size_t)tid * nb + tile);
+        sm.global_base[tid] = inc - tot + before;
     }
     __syncthreads();
 #pragma unroll
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t
                                                               const uint32_t* __restrict__ digit_totals, int n,
                                                               int shift, int nb) {
     __shared__ RadixSmem sm;
-    radix_scatter_tile<kIota, false>(sm, blockIdx.x, keys_in, vals_in, keys_out, vals_out, hist_scanned, digit_totals,
+    radix_scatter_tile<kIota, false, false>(sm, blockIdx.x, keys_in, vals_in, keys_out, vals_out, hist_scanned, digit_totals,
                                      n, shift, nb);
 }
 
@@ -348,47 +351,112 @@ struct Phase1Args {
     int P;
     const uint32_t* dkeys;
     const uint32_t* tiles_touched;
+    const uint32_t* key_bits;  // [0] OR, [1] AND of the visible depth keys
     uint32_t *keysB, *keysC, *valsA, *valsB, *hist, *totals, *sums;
     uint32_t *sorted_ids, *sorted_offsets;
 };
+
+// Up to this many radix tiles each block derives its own offsets straight from the
+// tile-major histogram (one coalesced column walk) instead of a separate row-scan phase
+// and its grid barrier.
+constexpr int kInBlockPrefixMaxTiles = 128;
 
 __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a) {
     __shared__ RadixSmem sm;
     cg::grid_group grid = cg::this_grid();
     const int n = a.P;
     const int nb = (n + kRadixTile - 1) / kRadixTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Bytes in which every visible key agrees need no pass.  (Invisible Gaussians carry
+    // key 0 and may end up anywhere: they emit no instances.)
+    const uint32_t vary = __ldcg(a.key_bits) ^ __ldcg(a.key_bits + 1);
+    int num_passes = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) num_passes += ((vary >> (8 * k)) & 0xffu) ? 1 : 0;
+    if (__ldcg(a.key_bits + 1) == 0xffffffffu && __ldcg(a.key_bits) == 0u) num_passes = 0;  // nothing visible
+    const bool in_block_prefix = nb <= kInBlockPrefixMaxTiles;
+    int ip = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = 8 * pass;
-        // ping-pong: keys dkeys->B->C->B->C, values iota->A->B->A->sorted_ids
-        const uint32_t* kin = pass == 0 ? a.dkeys : ((pass & 1) ? a.keysB : a.keysC);
-        uint32_t* kout = (pass & 1) ? a.keysC : a.keysB;
-        const uint32_t* vin = (pass & 1) ? a.valsA : a.valsB;
-        uint32_t* vout = pass == 3 ? a.sorted_ids : ((pass & 1) ? a.valsB : a.valsA);
-        for (int t = blockIdx.x; t < nb; t += gridDim.x)
-            radix_hist_tile<true>(sm.global_base, t, kin, n, shift, a.hist, nb);
-        grid.sync();
-        // row scan: one warp per digit row
-        for (int row = blockIdx.x * (kRadixThreads / 32) + warp; row < kRadixBins; row += gridDim.x * (kRadixThreads / 32)) {
-            uint32_t* r = a.hist + (size_t)row * nb;
-            uint32_t carry = 0;
-            for (int base = 0; base < nb; base += 32) {
-                const int j = base + lane;
-                const uint32_t v = j < nb ? __ldcg(r + j) : 0u;
-                const uint32_t inc = warp_inclusive_scan(v, lane);
-                if (j < nb) r[j] = carry + inc - v;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
+    for (int k = 0; k < 4; k++) {
+        const int shift = 8 * k;
+        if (num_passes == 0 || ((vary >> shift) & 0xffu) == 0) continue;  // grid-uniform
+        const bool first = ip == 0, last = ip == num_passes - 1;
+        // ping-pong: keys dkeys->B->C->B->C, values iota->A->B->A->..., last pass -> sorted_ids
+        const uint32_t* kin = first ? a.dkeys : ((ip & 1) ? a.keysB : a.keysC);
+        uint32_t* kout = (ip & 1) ? a.keysC : a.keysB;
+        const uint32_t* vin = (ip & 1) ? a.valsA : a.valsB;
+        uint32_t* vout = last ? a.sorted_ids : ((ip & 1) ? a.valsB : a.valsA);
+        if (in_block_prefix) {
+            // tile-major histogram: hist[tile * 256 + digit]
+            for (int t = blockIdx.x; t < nb; t += gridDim.x) {
+                const int base = t * kRadixTile;
+                uint32_t kk[kRadixItems];
+#pragma unroll
+                for (int i = 0; i < kRadixItems; i++) {
+                    const int j = base + i * kRadixThreads + tid;
+                    kk[i] = j < n ? __ldcg(kin + j) : 0u;
+                }
+                sm.global_base[tid] = 0;
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < kRadixItems; i++) {
+                    const int j = base + i * kRadixThreads + tid;
+                    if (j < n) atomicAdd(&sm.global_base[(kk[i] >> shift) & 0xffu], 1u);
+                }
+                __syncthreads();
+                a.hist[(size_t)t * kRadixBins + tid] = sm.global_base[tid];
+                __syncthreads();
             }
-            if (lane == 0) a.totals[row] = carry;
+            grid.sync();
+            for (int t = blockIdx.x; t < nb; t += gridDim.x) {
+                // digit `tid`: total over all tiles and prefix over the tiles before t
+                uint32_t total = 0, before = 0;
+                for (int b = 0; b < nb; b++) {
+                    const uint32_t v = __ldcg(a.hist + (size_t)b * kRadixBins + tid);
+                    total += v;
+                    before += b < t ? v : 0u;
+                }
+                // hand the per-tile scatter its two inputs through shared memory
+                sm.block_start[tid] = total;     // digit totals
+                sm.global_base[tid] = before;    // same digit, earlier tiles
+                __syncthreads();
+                if (first)
+                    radix_scatter_tile<true, true, true>(sm, t, kin, nullptr, kout, vout, nullptr, nullptr, n, shift, nb);
+                else
+                    radix_scatter_tile<false, true, true>(sm, t, kin, vin, kout, vout, nullptr, nullptr, n, shift, nb);
+            }
+            grid.sync();
+        } else {
+            for (int t = blockIdx.x; t < nb; t += gridDim.x)
+                radix_hist_tile<true>(sm.global_base, t, kin, n, shift, a.hist, nb);
+            grid.sync();
+            // row scan: one warp per digit row
+            for (int row = blockIdx.x * (kRadixThreads / 32) + warp; row < kRadixBins;
+                 row += gridDim.x * (kRadixThreads / 32)) {
+                uint32_t* r = a.hist + (size_t)row * nb;
+                uint32_t carry = 0;
+                for (int base = 0; base < nb; base += 32) {
+                    const int j = base + lane;
+                    const uint32_t v = j < nb ? __ldcg(r + j) : 0u;
+                    const uint32_t inc = warp_inclusive_scan(v, lane);
+                    if (j < nb) r[j] = carry + inc - v;
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) a.totals[row] = carry;
+            }
+            grid.sync();
+            for (int t = blockIdx.x; t < nb; t += gridDim.x) {
+                if (first)
+                    radix_scatter_tile<true, true, false>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
+                else
+                    radix_scatter_tile<false, true, false>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
+            }
+            grid.sync();
         }
-        grid.sync();
-        for (int t = blockIdx.x; t < nb; t += gridDim.x) {
-            if (pass == 0)
-                radix_scatter_tile<true, true>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
-            else
-                radix_scatter_tile<false, true>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
-        }
+        ip++;
+    }
+    if (num_passes == 0) {  // all visible keys identical (or nothing visible): identity order
+        for (int j = blockIdx.x * kRadixThreads + tid; j < n; j += gridDim.x * kRadixThreads) a.sorted_ids[j] = (uint32_t)j;
         grid.sync();
     }
     // exclusive scan of tiles_touched in depth order -> emission offsets
@@ -478,7 +546,7 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
     const int limit = coop_grid_limit();
     if (limit > 0) {
         Phase1Args k;
-        k.P = a.P; k.dkeys = dkeys; k.tiles_touched = a.tiles_touched;
+        k.P = a.P; k.dkeys = dkeys; k.tiles_touched = a.tiles_touched; k.key_bits = a.key_bits;
         k.keysB = keysB; k.keysC = keysC; k.valsA = valsA; k.valsB = valsB;
         k.hist = hist; k.totals = totals; k.sums = sums;
         k.sorted_ids = a.sorted_ids; k.sorted_offsets = a.sorted_offsets;

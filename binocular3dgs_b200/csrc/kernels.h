@@ -44,6 +44,7 @@ struct BinningPhase1Args {
     int P;
     const float* depths;            // sort key: float bits
     const uint32_t* tiles_touched;
+    const uint32_t* key_bits;       // [0] OR, [1] AND of the visible Gaussians' depth keys
     uint32_t* sorted_ids;           // out: Gaussian ids in (depth bits, id) order, P
     uint32_t* sorted_offsets;       // out: exclusive scan of tiles_touched in that order, P
     char* scratch;

@@ -276,13 +276,26 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
     }
     // R = sum(tiles_touched): warp shuffle reduce, one shared atomic per warp, one global
     // atomic per block — replaces the reference's full prefix sum + read of its last element.
-    __shared__ uint32_t s_total;
-    if (threadIdx.x == 0) s_total = 0;
+    // Also the OR and AND of the visible depth keys: bytes in which all keys agree need
+    // no radix pass (counter words: [0] R, [1] OR, [2] AND).
+    __shared__ uint32_t s_total, s_or, s_and;
+    if (threadIdx.x == 0) { s_total = 0; s_or = 0; s_and = 0xffffffffu; }
     __syncthreads();
-    uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
-    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_total, wsum);
+    const uint32_t dbits = __float_as_uint(depth);
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+    const uint32_t wor = __reduce_or_sync(0xffffffffu, tiles ? dbits : 0u);
+    const uint32_t wand = __reduce_and_sync(0xffffffffu, tiles ? dbits : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0 && wsum) {
+        atomicAdd(&s_total, wsum);
+        atomicOr(&s_or, wor);
+        atomicAnd(&s_and, wand);
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && s_total) atomicAdd(p.num_rendered, s_total);
+    if (threadIdx.x == 0 && s_total) {
+        atomicAdd(p.num_rendered, s_total);
+        atomicOr(p.num_rendered + 1, s_or);
+        atomicAnd(p.num_rendered + 2, s_and);
+    }
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ V,
