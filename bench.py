@@ -125,6 +125,11 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line (the JSON): anything libraries print there (e.g.
+    # NCCL's version banner) is sent to stderr instead.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -141,7 +146,8 @@ def main():
         from oracle import refbackend
         if not refbackend.available():
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdgr_ref.so was not built"}))
+                os.write(json_fd, (json.dumps({"impl": "reference", "unavailable":
+                                               "oracle/_ref/libdgr_ref.so was not built"}) + "\n").encode())
             return
         back = refbackend.reference()
     else:
@@ -396,7 +402,8 @@ def main():
         if args.impl == "reference":
             line["reference_kind"] = ("reference CUDA kernels (oracle/_ref, unmodified sources) on the same GPU; the "
                                       "reference has no CPU implementation of this path")
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
