@@ -374,6 +374,16 @@ def main():
         cpu_baseline = {"value": round(views / el, 4), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                         "sample": "%d views (fwd+bwd) of the same workload in %.1f s, OpenMP over tiles" % (views, el)}
 
+    # ---------------- §8(f) rank 1: fused photometric loss, timed beside the torch-style one
+    next_rows = None
+    if rank == 0 and world == 1 and args.impl == "native":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_loss
+            next_rows = {"photometric_loss": bench_loss.measure(dev, 3, H, W)}
+        except Exception as ex:  # never let the auxiliary row break the headline line
+            next_rows = {"photometric_loss": {"error": repr(ex)}}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -399,6 +409,8 @@ def main():
             line["kernels"] = kernels
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if next_rows:
+            line["next_rows"] = next_rows
         if args.impl == "reference":
             line["reference_kind"] = ("reference CUDA kernels (oracle/_ref, unmodified sources) on the same GPU; the "
                                       "reference has no CPU implementation of this path")

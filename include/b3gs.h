@@ -210,6 +210,29 @@ B3GS_API int b3gs_profile_num_stages(void);
 B3GS_API const char* b3gs_profile_stage_name(int i);
 B3GS_API int b3gs_profile_read(double* ms_total, unsigned long long* calls, int n);
 
+/*
+ * ---- fused photometric loss ---------------------------------
+ * loss = (1 - lambda) * mean|img1 - img2| + lambda * (1 - mean SSIM(img1, img2)), the loss
+ * the reference evaluates on the rasterizer's output every iteration (train.py:146-147;
+ * utils/loss_utils.py:18-21 l1_loss, :36-66 ssim/_ssim with the 11x11 sigma=1.5 window of
+ * :26-34, conv2d zero padding 5).  Images are float[C,H,W] (a batch is folded into C).
+ *
+ * b3gs_photometric_forward writes the three per-pixel partial derivatives of the SSIM
+ * map (w.r.t. mu1, E[x^2], E[xy]) needed by the backward, optionally the SSIM map itself
+ * (NULL to skip), and sums[0] = sum of the SSIM map, sums[1] = sum |img1 - img2| (device
+ * doubles, zeroed by the call).
+ * b3gs_photometric_backward writes dL/dimg1 = scales[0] * dSSIMsum/dimg1 +
+ * scales[1] * sign(img1 - img2); scales is a DEVICE float[2] so the upstream gradient
+ * never has to visit the host (for the combined loss: scales = {-lambda*g/(CHW),
+ * (1-lambda)*g/(CHW)}).  Gradient flows to img1 only.
+ */
+B3GS_API int b3gs_photometric_forward(int C, int H, int W, const float* img1, const float* img2, float* dm_dmu1,
+                                      float* dm_dsigma1_sq, float* dm_dsigma12, float* ssim_map, double* sums,
+                                      void* stream);
+B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, const float* img2,
+                                       const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                                       const float* scales, float* dL_dimg1, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
 

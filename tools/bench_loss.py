@@ -1,0 +1,89 @@
+"""Timing of the fused photometric loss against the same loss
+written the way the reference writes it (utils/loss_utils.py: five depthwise conv2d +
+elementwise ops, autograd backward), both on the GPU, CUDA events, L2 flushed between
+iterations.  Used by bench.py ("next_rows") and runnable on its own."""
+import os
+import sys
+from math import exp
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _torch_style_loss(img, gt, lam=0.2):
+    """What train.py:146-147 + utils/loss_utils.py:36-66 execute (restated, same ops)."""
+    C = img.size(-3)
+    g = torch.Tensor([exp(-(x - 11 // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    g = (g / g.sum()).unsqueeze(1)
+    w = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(C, 1, 11, 11).contiguous().to(img.device)
+    mu1, mu2 = F.conv2d(img, w, padding=5, groups=C), F.conv2d(gt, w, padding=5, groups=C)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img * img, w, padding=5, groups=C) - mu1_sq
+    s2 = F.conv2d(gt * gt, w, padding=5, groups=C) - mu2_sq
+    s12 = F.conv2d(img * gt, w, padding=5, groups=C) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim = (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+    return (1.0 - lam) * torch.abs(img - gt).mean() + lam * (1.0 - ssim)
+
+
+def measure(dev, C=3, H=800, W=800, iters=30, warmup=5):
+    from binocular3dgs_b200 import losses
+    g = torch.Generator().manual_seed(0)
+    gt = torch.rand(C, H, W, generator=g).to(dev)
+    img = (gt + 0.05 * torch.randn(C, H, W, generator=g).to(dev)).clamp(0, 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run(fn):
+        ts = []
+        for i in range(warmup + iters):
+            a = img.clone().requires_grad_(True)
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            v = fn(a, gt)
+            v.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2], float(v.detach()), a.grad
+
+    # the two kernels alone, through the C-ABI on preallocated buffers
+    fns = losses._fns()
+    maps = torch.empty((3, C, H, W), device=dev)
+    sums = torch.empty(2, dtype=torch.float64, device=dev)
+    scales = torch.tensor([-0.2 / (C * H * W), 0.8 / (C * H * W)], device=dev)
+    grad = torch.empty((C, H, W), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    kt = []
+    for i in range(warmup + iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fns.b3gs_photometric_forward(C, H, W, img.data_ptr(), gt.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr(),
+                                     maps[2].data_ptr(), None, sums.data_ptr(), st)
+        fns.b3gs_photometric_backward(C, H, W, img.data_ptr(), gt.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr(),
+                                      maps[2].data_ptr(), scales.data_ptr(), grad.data_ptr(), st)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            kt.append(e0.elapsed_time(e1))
+    t_kernels = sorted(kt)[len(kt) // 2]
+    t_fused, v_fused, g_fused = run(lambda a, b: losses.photometric_loss(a, b, 0.2))
+    t_torch, v_torch, g_torch = run(_torch_style_loss)
+    n = C * H * W
+    alg_bytes = n * (4 * 2 + 4 * 3) + n * (4 * 5 + 4)     # fwd: 2 reads + 3 writes; bwd: 5 reads + 1 write
+    return {"what": "0.8*L1 + 0.2*(1-SSIM) forward+backward, %dx%dx%d" % (C, H, W), "fused_ms": round(t_fused, 4),
+            "torch_reference_style_ms": round(t_torch, 4), "speedup": round(t_torch / t_fused, 2),
+            "kernels_only_ms": round(t_kernels, 4), "alg_bytes": alg_bytes,
+            "kernels_GBps": round(alg_bytes / t_kernels / 1e6, 1),
+            "value_abs_diff": abs(v_fused - v_torch),
+            "grad_rel_diff": float((g_fused - g_torch).abs().max() / g_torch.abs().max())}
+
+
+if __name__ == "__main__":
+    import json
+    print(json.dumps(measure(torch.device("cuda:0"))))
