@@ -151,23 +151,27 @@ static int radix_blocks(int n) { return (n + kRadixTile - 1) / kRadixTile; }
 
 // Loads of data another block wrote earlier IN THE SAME (cooperative) kernel must not
 // use the non-coherent path; everything else may.
-template <bool kCoop>
-__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) {
+template <bool kCoop, typename T>
+__device__ __forceinline__ T ld_u32(const T* p) {
     return kCoop ? __ldcg(p) : __ldg(p);
 }
 
-struct RadixSmem {
+// KeyT is uint32_t for the depth sort and uint16_t for the tile sort (tile ids < 65536:
+// 6 instead of 8 bytes per instance and pass).
+template <typename KeyT>
+struct RadixSmemT {
     uint32_t warp_cnt[kRadixThreads / 32][kRadixBins];  // 8 KB
     uint32_t global_base[kRadixBins];
     uint32_t block_start[kRadixBins];
     uint32_t scan[32];
-    uint32_t keys[kRadixTile];  // 16 KB
+    KeyT keys[kRadixTile];      // 16 or 8 KB
     uint32_t vals[kRadixTile];  // 16 KB
 };
+typedef RadixSmemT<uint32_t> RadixSmem;
 
 // hist[d * nb + tile] = number of keys of `tile` with digit d.  s_cnt: 256 words.
-template <bool kCoop>
-__device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const uint32_t* __restrict__ keys, int n,
+template <bool kCoop, typename KeyT>
+__device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const KeyT* __restrict__ keys, int n,
                                                 int shift, uint32_t* __restrict__ hist, int nb) {
     const int base = tile * kRadixTile;
     // all 16 loads in flight before the first shared atomic (one memory round trip)
@@ -175,7 +179,7 @@ __device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const
 #pragma unroll
     for (int i = 0; i < kRadixItems; i++) {
         const int j = base + i * kRadixThreads + threadIdx.x;
-        k[i] = j < n ? ld_u32<kCoop>(keys + j) : 0u;
+        k[i] = j < n ? (uint32_t)ld_u32<kCoop>(keys + j) : 0u;
     }
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -189,27 +193,34 @@ __device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRadixThreads) radix_hist(const uint32_t* __restrict__ keys, int n, int shift,
+template <typename KeyT>
+__global__ void __launch_bounds__(kRadixThreads) radix_hist(const KeyT* __restrict__ keys, int n, int shift,
                                                            uint32_t* __restrict__ hist, int nb) {
     __shared__ uint32_t s_cnt[kRadixBins];
-    radix_hist_tile<false>(s_cnt, blockIdx.x, keys, n, shift, hist, nb);
+    radix_hist_tile<false, KeyT>(s_cnt, blockIdx.x, keys, n, shift, hist, nb);
 }
 
 // One block per digit: exclusive scan of the digit's row over blocks, row total out.
+// Blocked arrangement: each thread owns a contiguous slice of the row, so a row of any
+// length costs ONE block-wide scan (the first version looped a block scan per 256
+// entries: 36 us for 10k tiles).
 __global__ void __launch_bounds__(256) radix_rowscan(uint32_t* __restrict__ hist, int nb,
                                                     uint32_t* __restrict__ digit_totals) {
     __shared__ uint32_t s_warp[32];
     uint32_t* row = hist + (size_t)blockIdx.x * nb;
-    uint32_t carry = 0;
-    for (int base = 0; base < nb; base += 256) {
-        const int j = base + threadIdx.x;
-        const uint32_t v = j < nb ? row[j] : 0;
-        uint32_t total;
-        const uint32_t inc = block_inclusive_scan(v, s_warp, total);
-        if (j < nb) row[j] = carry + inc - v;
-        carry += total;
+    const int per = (nb + 255) / 256;
+    const int lo = min(nb, (int)threadIdx.x * per), hi = min(nb, lo + per);
+    uint32_t acc = 0;
+    for (int j = lo; j < hi; j++) acc += row[j];
+    uint32_t total;
+    const uint32_t inc = block_inclusive_scan(acc, s_warp, total);
+    uint32_t run = inc - acc;
+    for (int j = lo; j < hi; j++) {
+        const uint32_t v = row[j];
+        row[j] = run;
+        run += v;
     }
-    if (threadIdx.x == 0) digit_totals[blockIdx.x] = carry;
+    if (threadIdx.x == 0) digit_totals[blockIdx.x] = total;
 }
 
 // Lanes of the warp holding the same 8-bit digit.  Eight ballots, constant time;
@@ -228,10 +239,10 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
 // Stable rank-and-scatter of one 4096-key tile.  kIota: values are the key indices.
 // kPreloaded: the caller already put the digit totals in sm.block_start[] and the
 // same-digit-earlier-tiles prefix in sm.global_base[] (cooperative in-block-prefix path).
-template <bool kIota, bool kCoop, bool kPreloaded>
-__device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, const uint32_t* __restrict__ keys_in,
+template <bool kIota, bool kCoop, bool kPreloaded, typename KeyT>
+__device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT>& sm, int tile, const KeyT* __restrict__ keys_in,
                                                    const uint32_t* __restrict__ vals_in,
-                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                   KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                    const uint32_t* __restrict__ hist_scanned,
                                                    const uint32_t* __restrict__ digit_totals, int n, int shift,
                                                    int nb) {
@@ -246,7 +257,7 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, cons
     for (int r = 0; r < kRadixItems; r++) {
         const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
         const bool valid = j < n;
-        k[r] = valid ? ld_u32<kCoop>(keys_in + j) : 0xffffffffu;
+        k[r] = valid ? (uint32_t)ld_u32<kCoop>(keys_in + j) : 0xffffffffu;
         v[r] = valid ? (kIota ? (uint32_t)j : ld_u32<kCoop>(vals_in + j)) : 0u;
     }
 #pragma unroll
@@ -295,7 +306,7 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, cons
         const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
         const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
         const uint32_t pos = sm.block_start[d] + sm.warp_cnt[warp][d] + rk;
-        sm.keys[pos] = k[r];
+        sm.keys[pos] = (KeyT)k[r];
         sm.vals[pos] = v[r];
     }
     __syncthreads();
@@ -304,37 +315,38 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmem& sm, int tile, cons
         const uint32_t key = sm.keys[i];
         const uint32_t d = (key >> shift) & 0xffu;
         const uint32_t g = sm.global_base[d] + ((uint32_t)i - sm.block_start[d]);
-        keys_out[g] = key;
+        keys_out[g] = (KeyT)key;
         vals_out[g] = sm.vals[i];
     }
     __syncthreads();
 }
 
-template <bool kIota>
-__global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const uint32_t* __restrict__ keys_in,
+template <bool kIota, typename KeyT>
+__global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter(const KeyT* __restrict__ keys_in,
                                                               const uint32_t* __restrict__ vals_in,
-                                                              uint32_t* __restrict__ keys_out,
+                                                              KeyT* __restrict__ keys_out,
                                                               uint32_t* __restrict__ vals_out,
                                                               const uint32_t* __restrict__ hist_scanned,
                                                               const uint32_t* __restrict__ digit_totals, int n,
                                                               int shift, int nb) {
-    __shared__ RadixSmem sm;
-    radix_scatter_tile<kIota, false, false>(sm, blockIdx.x, keys_in, vals_in, keys_out, vals_out, hist_scanned, digit_totals,
-                                     n, shift, nb);
+    __shared__ RadixSmemT<KeyT> sm;
+    radix_scatter_tile<kIota, false, false, KeyT>(sm, blockIdx.x, keys_in, vals_in, keys_out, vals_out, hist_scanned,
+                                                  digit_totals, n, shift, nb);
 }
 
 // One stable 8-bit pass.  scratch: hist u32[256*nb] + digit_totals u32[256].
-static void radix_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+template <typename KeyT>
+static void radix_pass(const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
                        uint32_t* hist, uint32_t* digit_totals, int n, int shift, bool iota, cudaStream_t stream) {
     const int nb = radix_blocks(n);
-    radix_hist<<<nb, kRadixThreads, 0, stream>>>(keys_in, n, shift, hist, nb);
+    radix_hist<KeyT><<<nb, kRadixThreads, 0, stream>>>(keys_in, n, shift, hist, nb);
     radix_rowscan<<<kRadixBins, 256, 0, stream>>>(hist, nb, digit_totals);
     if (iota)
-        radix_scatter<true><<<nb, kRadixThreads, 0, stream>>>(keys_in, nullptr, keys_out, vals_out, hist, digit_totals,
-                                                            n, shift, nb);
+        radix_scatter<true, KeyT><<<nb, kRadixThreads, 0, stream>>>(keys_in, nullptr, keys_out, vals_out, hist,
+                                                                  digit_totals, n, shift, nb);
     else
-        radix_scatter<false><<<nb, kRadixThreads, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, hist,
-                                                             digit_totals, n, shift, nb);
+        radix_scatter<false, KeyT><<<nb, kRadixThreads, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, hist,
+                                                                   digit_totals, n, shift, nb);
     count_launch(3);
 }
 
@@ -421,14 +433,14 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
                 sm.global_base[tid] = before;    // same digit, earlier tiles
                 __syncthreads();
                 if (first)
-                    radix_scatter_tile<true, true, true>(sm, t, kin, nullptr, kout, vout, nullptr, nullptr, n, shift, nb);
+                    radix_scatter_tile<true, true, true, uint32_t>(sm, t, kin, nullptr, kout, vout, nullptr, nullptr, n, shift, nb);
                 else
-                    radix_scatter_tile<false, true, true>(sm, t, kin, vin, kout, vout, nullptr, nullptr, n, shift, nb);
+                    radix_scatter_tile<false, true, true, uint32_t>(sm, t, kin, vin, kout, vout, nullptr, nullptr, n, shift, nb);
             }
             grid.sync();
         } else {
             for (int t = blockIdx.x; t < nb; t += gridDim.x)
-                radix_hist_tile<true>(sm.global_base, t, kin, n, shift, a.hist, nb);
+                radix_hist_tile<true, uint32_t>(sm.global_base, t, kin, n, shift, a.hist, nb);
             grid.sync();
             // row scan: one warp per digit row
             for (int row = blockIdx.x * (kRadixThreads / 32) + warp; row < kRadixBins;
@@ -447,9 +459,9 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
             grid.sync();
             for (int t = blockIdx.x; t < nb; t += gridDim.x) {
                 if (first)
-                    radix_scatter_tile<true, true, false>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
+                    radix_scatter_tile<true, true, false, uint32_t>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
                 else
-                    radix_scatter_tile<false, true, false>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
+                    radix_scatter_tile<false, true, false, uint32_t>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
             }
             grid.sync();
         }
@@ -564,10 +576,10 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
     }
     // 4 stable passes over float_bits(depth); depth > 0.2 for every visible Gaussian so
     // unsigned order == float order, and the reference sorts the raw bits anyway.
-    radix_pass(dkeys, nullptr, keysB, valsA, hist, totals, a.P, 0, true, stream);
-    radix_pass(keysB, valsA, keysC, valsB, hist, totals, a.P, 8, false, stream);
-    radix_pass(keysC, valsB, keysB, valsA, hist, totals, a.P, 16, false, stream);
-    radix_pass(keysB, valsA, keysC, a.sorted_ids, hist, totals, a.P, 24, false, stream);
+    radix_pass<uint32_t>(dkeys, nullptr, keysB, valsA, hist, totals, a.P, 0, true, stream);
+    radix_pass<uint32_t>(keysB, valsA, keysC, valsB, hist, totals, a.P, 8, false, stream);
+    radix_pass<uint32_t>(keysC, valsB, keysB, valsA, hist, totals, a.P, 16, false, stream);
+    radix_pass<uint32_t>(keysB, valsA, keysC, a.sorted_ids, hist, totals, a.P, 24, false, stream);
     // emission offsets in depth order
     exclusive_scan_gather(a.tiles_touched, a.sorted_ids, a.sorted_offsets, sums, nullptr, a.P, stream);
     return cudaGetLastError();
@@ -576,13 +588,15 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
 // ------------------------------------------------------------------ phase 2 (R-sized)
 // One warp per 32 depth-ordered Gaussians.  The warp's instances form one contiguous run
 // of the output (their offsets are an exclusive scan), so lane L writes instances
-// L, L+32, ... of that run: every lane is busy whatever the rectangle sizes are and the
-// stores are fully coalesced.  The owning Gaussian of an instance is found by a 5-step
-// binary search over the 32 lanes' offsets (shuffles).
+// t0+L of that run, 32 at a time: every lane is busy whatever the rectangle sizes are and
+// the stores are fully coalesced.  Gaussians with tiles are first compacted to the low
+// lanes; the owner of each instance in a 32-wide window then costs one REDUX.OR (a bit
+// per Gaussian starting inside the window) and one POPC per lane.
+template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_instances(int P, const uint32_t* __restrict__ sorted_ids,
                                                      const uint32_t* __restrict__ sorted_offsets,
                                                      const float4* __restrict__ records, const int* __restrict__ radii,
-                                                     uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ ids,
+                                                     KeyT* __restrict__ tile_keys, uint32_t* __restrict__ ids,
                                                      int grid_x, int grid_y) {
     const unsigned full = 0xffffffffu;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -601,58 +615,58 @@ __global__ void __launch_bounds__(256) emit_instances(int P, const uint32_t* __r
             cnt = w * (y1 - y0);
         }
     }
-    // offsets relative to the warp's first instance
-    const uint32_t warp_begin = __shfl_sync(full, off, 0);
-    uint32_t rel = (i < P) ? off - warp_begin : 0u;
-    uint32_t warp_total = (i < P) ? rel + (uint32_t)cnt : 0u;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) warp_total = max(warp_total, __shfl_xor_sync(full, warp_total, d));
-    if (i >= P) rel = warp_total;  // sentinel: never selected by the search below
-    const float inv_w = 1.0f / (float)w;
-    // warp-uniform trip count: every lane takes part in every shuffle
+    const unsigned nz = __ballot_sync(full, cnt > 0);
+    if (nz == 0) return;
+    const int nnz = __popc(nz);
+    // compact the Gaussians that own tiles to lanes 0..nnz-1 (offsets strictly increase there)
+    const uint32_t warp_begin = __shfl_sync(full, off, __ffs(nz) - 1);
+    const uint32_t last = 31 - __clz(nz);
+    const uint32_t warp_total = __shfl_sync(full, off + (uint32_t)cnt, last) - warp_begin;
+    const unsigned src = __fns(nz, 0, lane + 1);  // lane of the (lane+1)-th set bit, or ~0
+    const int s = src < 32 ? (int)src : 0;
+    uint32_t crel = __shfl_sync(full, off, s) - warp_begin;
+    const uint32_t cxy = __shfl_sync(full, (uint32_t)x0 | ((uint32_t)y0 << 16), s);
+    const uint32_t cw = __shfl_sync(full, (uint32_t)w, s);
+    const uint32_t cg = __shfl_sync(full, g, s);
+    if (lane >= nnz) crel = 0xffffffffu;  // never starts inside a window
+    uint32_t below = 0;  // compacted Gaussians starting before the window
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
     for (uint32_t t0 = 0; t0 < warp_total; t0 += 32) {
+        const uint32_t d = crel - t0;  // wraps for starts before the window
+        const unsigned starts = __reduce_or_sync(full, d < 32u ? (1u << d) : 0u);
+        const int owner = (int)below + __popc(starts & le_mask) - 1;
+        below += __popc(starts);
         const uint32_t t = t0 + lane;
-        // largest lane j with rel[j] <= t (zero-count Gaussians share their successor's
-        // offset, so the search lands on the one that owns instance t)
-        int j = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const uint32_t o = __shfl_sync(full, rel, j + step);
-            if (o <= t) j += step;
-        }
-        const uint32_t local = t - __shfl_sync(full, rel, j);
-        const int sw = __shfl_sync(full, w, j);
-        const int sx0 = __shfl_sync(full, x0, j), sy0 = __shfl_sync(full, y0, j);
-        const uint32_t sg = __shfl_sync(full, g, j);
-        const float siw = __shfl_sync(full, inv_w, j);
+        const uint32_t orel = __shfl_sync(full, crel, owner & 31);
+        const uint32_t oxy = __shfl_sync(full, cxy, owner & 31);
+        const uint32_t ow = __shfl_sync(full, cw, owner & 31);
+        const uint32_t og = __shfl_sync(full, cg, owner & 31);
         if (t < warp_total) {
-            // local / sw for local < 2^22: float quotient, corrected by one step either way
-            int ty = (int)(((float)local + 0.5f) * siw);
-            int tx = (int)local - ty * sw;
-            if (tx < 0) { ty--; tx += sw; }
-            if (tx >= sw) { ty++; tx -= sw; }
-            tile_keys[warp_begin + t] = (uint32_t)((sy0 + ty) * grid_x + sx0 + tx);
-            ids[warp_begin + t] = sg;
+            const uint32_t local = t - orel;
+            // local / ow for local < 2^22: float quotient, corrected by one step either way
+            int ty = (int)(((float)local + 0.5f) * __frcp_rn((float)ow));
+            int tx = (int)local - ty * (int)ow;
+            if (tx < 0) { ty--; tx += (int)ow; }
+            if (tx >= (int)ow) { ty++; tx -= (int)ow; }
+            tile_keys[warp_begin + t] = (KeyT)(((oxy >> 16) + ty) * grid_x + (oxy & 0xffffu) + tx);
+            ids[warp_begin + t] = og;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) tile_ranges_u32(int R, const uint32_t* __restrict__ tile_keys,
-                                                      uint2* __restrict__ ranges) {
-    // 4 consecutive keys per thread (one 16-byte load) plus the predecessor of the first
-    const int base = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+template <typename KeyT>
+__global__ void __launch_bounds__(256) tile_ranges_k(int R, const KeyT* __restrict__ tile_keys,
+                                                    uint2* __restrict__ ranges) {
+    // 8 consecutive keys per thread plus the predecessor of the first
+    constexpr int kPer = 8;
+    const int base = (blockIdx.x * blockDim.x + threadIdx.x) * kPer;
     if (base >= R) return;
-    uint32_t k[4];
-    if (base + 3 < R) {
-        const uint4 q = *reinterpret_cast<const uint4*>(tile_keys + base);
-        k[0] = q.x; k[1] = q.y; k[2] = q.z; k[3] = q.w;
-    } else {
+    uint32_t k[kPer];
 #pragma unroll
-        for (int i = 0; i < 4; i++) k[i] = base + i < R ? tile_keys[base + i] : 0u;
-    }
-    uint32_t prev = base > 0 ? tile_keys[base - 1] : 0u;
+    for (int i = 0; i < kPer; i++) k[i] = base + i < R ? (uint32_t)__ldg(tile_keys + base + i) : 0u;
+    uint32_t prev = base > 0 ? (uint32_t)__ldg(tile_keys + base - 1) : 0u;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < kPer; i++) {
         const int idx = base + i;
         if (idx >= R) break;
         const uint32_t cur = k[i];
@@ -741,6 +755,36 @@ size_t binning_phase2_scratch_bytes(int R) {
     return align_up(r * 4, 256) * 3 + align_up(radix_scratch_elems(R) * 4, 256);
 }
 
+// emit + stable sort by tile id + ranges.  scratch: keysA[R] keysB[R] (KeyT) idsB[R] hist
+template <typename KeyT>
+static cudaError_t tile_sort(const BinningPhase2Args& a, char* q, cudaStream_t stream) {
+    const int T = a.grid_x * a.grid_y;
+    const size_t r = (size_t)a.R;
+    KeyT* keysA = reinterpret_cast<KeyT*>(q); q += align_up(r * sizeof(KeyT), 256);
+    KeyT* keysB = reinterpret_cast<KeyT*>(q); q += align_up(r * sizeof(KeyT), 256);
+    uint32_t* idsB = reinterpret_cast<uint32_t*>(q);  q += align_up(r * 4, 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(q);
+    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.R);
+    // ping-pong so that the LAST pass writes the ids into point_list
+    const int passes = tile_passes(T);
+    uint32_t* ids_cur = (passes & 1) ? idsB : a.point_list;  // where emission writes
+    uint32_t* ids_oth = (passes & 1) ? a.point_list : idsB;
+    KeyT* keys_cur = keysA;
+    KeyT* keys_oth = keysB;
+    emit_instances<KeyT><<<(a.P + 255) / 256, 256, 0, stream>>>(a.P, a.sorted_ids, a.sorted_offsets, a.records, a.radii,
+                                                               keys_cur, ids_cur, a.grid_x, a.grid_y);
+    count_launch();
+    for (int p = 0; p < passes; p++) {
+        radix_pass<KeyT>(keys_cur, ids_cur, keys_oth, ids_oth, hist, totals, a.R, 8 * p, false, stream);
+        KeyT* t = keys_cur; keys_cur = keys_oth; keys_oth = t;
+        uint32_t* u = ids_cur; ids_cur = ids_oth; ids_oth = u;
+    }
+    // ids_cur == a.point_list by construction
+    tile_ranges_k<KeyT><<<(a.R + 2047) / 2048, 256, 0, stream>>>(a.R, keys_cur, a.ranges);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream) {
     const int T = a.grid_x * a.grid_y;
     cudaError_t e = cudaMemsetAsync(a.ranges, 0, (size_t)T * sizeof(uint2), stream);
@@ -763,29 +807,7 @@ cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream) 
         count_launch(10);
         return cudaGetLastError();
     }
-    uint32_t* keysA = reinterpret_cast<uint32_t*>(q); q += align_up(r * 4, 256);
-    uint32_t* keysB = reinterpret_cast<uint32_t*>(q); q += align_up(r * 4, 256);
-    uint32_t* idsB = reinterpret_cast<uint32_t*>(q);  q += align_up(r * 4, 256);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(q);
-    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.R);
-    // ping-pong so that the LAST pass writes the ids into point_list
-    const int passes = tile_passes(T);
-    uint32_t* ids_cur = (passes & 1) ? idsB : a.point_list;  // where emission writes
-    uint32_t* ids_oth = (passes & 1) ? a.point_list : idsB;
-    uint32_t* keys_cur = keysA;
-    uint32_t* keys_oth = keysB;
-    emit_instances<<<(a.P + 255) / 256, 256, 0, stream>>>(a.P, a.sorted_ids, a.sorted_offsets, a.records, a.radii,
-                                                         keys_cur, ids_cur, a.grid_x, a.grid_y);
-    count_launch();
-    for (int p = 0; p < passes; p++) {
-        radix_pass(keys_cur, ids_cur, keys_oth, ids_oth, hist, totals, a.R, 8 * p, false, stream);
-        uint32_t* t = keys_cur; keys_cur = keys_oth; keys_oth = t;
-        t = ids_cur; ids_cur = ids_oth; ids_oth = t;
-    }
-    // ids_cur == a.point_list by construction
-    tile_ranges_u32<<<(a.R + 1023) / 1024, 256, 0, stream>>>(a.R, keys_cur, a.ranges);
-    count_launch();
-    return cudaGetLastError();
+    return T <= 65536 ? tile_sort<uint16_t>(a, q, stream) : tile_sort<uint32_t>(a, q, stream);
 }
 
 }  // namespace b3

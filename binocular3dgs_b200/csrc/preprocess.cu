@@ -113,7 +113,7 @@ __device__ __forceinline__ float cull_threshold(float px, float py, float cx, fl
     return 1.01f * logf(255.0f * o) + 0.05f;
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
+__global__ void __launch_bounds__(256, 5) preprocess_kernel(PreParams p) {
     __shared__ float s_mean[256 * 3];
     __shared__ float s_scale[256 * 3];
     const int base = blockIdx.x * 256;

@@ -53,7 +53,7 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
     c[5] = M.m[2][0] * M.m[2][0] + M.m[2][1] * M.m[2][1] + M.m[2][2] * M.m[2][2];
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackwardArgs p) {
+__global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackwardArgs p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
     const size_t i = (size_t)idx;
