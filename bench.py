@@ -383,6 +383,10 @@ def main():
             next_rows = {"photometric_loss": bench_loss.measure(dev, 3, H, W)}
         except Exception as ex:  # never let the auxiliary row break the headline line
             next_rows = {"photometric_loss": {"error": repr(ex)}}
+        try:  # §8(f) rank 2 at the size of the config that uses it (LLFF fern, 1008x756)
+            next_rows["binocular_loss"] = bench_loss.measure_binocular(dev)
+        except Exception as ex:
+            next_rows["binocular_loss"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

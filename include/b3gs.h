@@ -233,6 +233,47 @@ B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, c
                                        const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
                                        const float* scales, float* dL_dimg1, void* stream);
 
+/*
+ * ---- binocular-consistency loss -------------------------------
+ * What train.py:122-136 evaluates after shift_cam_start on the two renders of a stereo
+ * pair:   disparity = k_disp / (depth + 1e-5),  k_disp = focal_x * (-trans_dist);
+ *         warped = inverse_warp_images(shifted, disparity), mask = the same warp of ones
+ *         (utils/graphics_utils.py:80-125);
+ *         loss = l1_loss(warped, gt, mask) + w * SmoothLoss(disparity * mask, gt)
+ *         (utils/loss_utils.py:18-21, :68-91; w = 0.05).
+ * Images are float[3,H,W], depth float[H,W]; H, W >= 3.
+ *
+ * b3gs_binocular_forward zeroes and fills sums[3] (device doubles): [0] = sum over
+ * 3*H*W of |warped*mask - gt*mask|, [1] / [2] = sums over (H-2)(W-2) of the x / y
+ * smoothness terms; the caller forms loss = sums[0]/(3HW) + w*(sums[1]+sums[2])/((H-2)(W-2)).
+ * b3gs_binocular_backward recomputes from the same inputs (nothing is saved) and writes
+ * dL/dshifted (zeroed by the call, accumulated with float REDs) and dL/ddepth;
+ * scales is a DEVICE float[2] = {g/(3HW), g*w/((H-2)(W-2))} so the upstream gradient g
+ * never visits the host.  Gradient flows to `shifted` and `depth` only.
+ */
+B3GS_API int b3gs_binocular_forward(int H, int W, const float* shifted, const float* depth, const float* gt,
+                                    float k_disp, double* sums, void* stream);
+B3GS_API int b3gs_binocular_backward(int H, int W, const float* shifted, const float* depth, const float* gt,
+                                     float k_disp, const float* scales, float* dL_dshifted, float* dL_ddepth,
+                                     void* stream);
+
+/* The constituents as stand-alone operators (drop-in for the reference's Python API).
+ * b3gs_warp_*: inverse_warp_images for one image float[C,H,W] and one disparity map
+ * float[H,W] (utils/graphics_utils.py:80-125); the backward zeroes dL_dimage and
+ * accumulates into it; dL_ddisparity may be NULL.
+ * b3gs_smooth_*: SmoothLoss.forward(disparity float[H,W], image float[3,H,W])
+ * (utils/loss_utils.py:68-91): sums[2] (device doubles, zeroed by the call) = x / y sums
+ * over (H-2)(W-2); the backward writes dL/ddisparity = scale[0] * d(sums[0]+sums[1])/
+ * d(disparity) with scale a DEVICE float[1]. */
+B3GS_API int b3gs_warp_forward(int C, int H, int W, const float* image, const float* disparity, float* warped,
+                               void* stream);
+B3GS_API int b3gs_warp_backward(int C, int H, int W, const float* image, const float* disparity,
+                                const float* dL_dwarped, float* dL_dimage, float* dL_ddisparity, void* stream);
+B3GS_API int b3gs_smooth_forward(int H, int W, const float* disparity, const float* image, double* sums,
+                                 void* stream);
+B3GS_API int b3gs_smooth_backward(int H, int W, const float* disparity, const float* image, const float* scale,
+                                  float* dL_ddisparity, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
 

@@ -1,0 +1,184 @@
+"""Binocular-consistency loss.
+
+CPU: the float64 numpy oracle (oracle/binocular_oracle.py) against golden vectors produced
+by the reference's own inverse_warp_images / l1_loss / SmoothLoss run as train.py:128-136
+runs them (tests/golden/make_binocular_golden.py), values and gradients, and — when the
+reference checkout is present — against the reference live.
+GPU (-m gpu): the CUDA kernels through the C-ABI against the same golden vectors (fused
+loss and the two stand-alone operators), and at full size against the oracle.
+
+Tolerances: the reference computes in float32; the warp itself is a two-tap blend
+(1e-6 absolute on images in [0,1]); loss values 2e-6; gradients 2e-5 of the tensor's max
+magnitude (float32 sums of up to 6 REDs per pixel in arbitrary order)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import binocular_oracle as bo
+
+WARP_TOL, VAL_TOL, GRAD_TOL = 1e-6, 2e-6, 2e-5
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_binocular_golden",
+                                              os.path.join(HERE, "golden", "make_binocular_golden.py"))
+mbg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mbg)
+NAMES = sorted(mbg.CASES)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def load(name):
+    c = mbg.CASES[name]
+    return c, np.load(os.path.join(HERE, "golden", name + ".npz")), mbg.make_inputs(**c)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_reference_golden(name):
+    c, g, (shifted, depth, gt) = load(name)
+    s, d, t = shifted.numpy(), depth.numpy()[0], gt.numpy()
+    f, td = c["focal_x"], c["trans_dist"]
+    disp = bo.disparity_of(d, f, td)
+    mask = bo.inverse_warp(np.ones((1,) + disp.shape), disp)[0]
+    assert np.abs(bo.inverse_warp(s, disp) - g["warped"]).max() < WARP_TOL
+    assert np.abs(mask - g["shift_mask"]).max() < WARP_TOL
+    assert ((mask != 0) == (g["shift_mask"] != 0)).all()
+    l1, sm = bo.binocular_terms(s, d, t, f, td)
+    assert abs(l1 - float(g["l1"])) < VAL_TOL and abs(sm - float(g["smooth"])) < VAL_TOL * max(1.0, sm)
+    assert abs(bo.binocular_loss(s, d, t, f, td) - float(g["loss"])) < VAL_TOL
+    gi, gd = bo.binocular_loss_grad(s, d, t, f, td)
+    assert rel(gi, g["grad_shifted"]) < GRAD_TOL and rel(gd, g["grad_depth"][0]) < GRAD_TOL
+    gi, gd = bo.inverse_warp_grad(s, disp, g["warp_up"])
+    assert rel(gi, g["warp_grad_image"]) < GRAD_TOL and rel(gd, g["warp_grad_disparity"][0]) < GRAD_TOL
+    assert rel(bo.smooth_loss_grad(disp * mask, t), g["smooth_grad_disparity"][0]) < GRAD_TOL
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils"), reason="reference checkout not present")
+def test_oracle_matches_reference_live(monkeypatch):
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.syspath_prepend("/root/reference")
+    import sys
+    for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+        monkeypatch.delitem(sys.modules, k, raising=False)
+    from utils.graphics_utils import inverse_warp_images
+    from utils.loss_utils import SmoothLoss, l1_loss
+    c = dict(H=23, W=31, seed=77, focal_x=50.0, trans_dist=-0.37, depth_lo=1.0, depth_hi=4.0)
+    shifted, depth, gt = mbg.make_inputs(**c)
+    loss = mbg.reference_loss((inverse_warp_images, SmoothLoss, l1_loss), shifted, depth, gt, c["focal_x"],
+                              c["trans_dist"])[0]
+    mine = bo.binocular_loss(shifted.numpy(), depth.numpy()[0], gt.numpy(), c["focal_x"], c["trans_dist"])
+    assert abs(float(loss) - mine) < VAL_TOL
+
+
+def test_oracle_gradient_is_the_derivative_of_the_oracle_loss():
+    """Central finite differences in float64 at points away from the floor() jumps."""
+    c = dict(H=9, W=12, seed=3, focal_x=20.0, trans_dist=0.3, depth_lo=2.0, depth_hi=5.0)
+    shifted, depth, gt = (t.numpy().astype(np.float64) for t in mbg.make_inputs(**c))
+    depth = depth[0]
+    f, td = c["focal_x"], c["trans_dist"]
+    gi, gd = bo.binocular_loss_grad(shifted, depth, gt, f, td)
+    rng = np.random.default_rng(0)
+    h = 1e-7
+    for _ in range(20):
+        y, x, ch = rng.integers(9), rng.integers(12), rng.integers(3)
+        for arr, idx, grad in ((shifted, (ch, y, x), gi), (depth, (y, x), gd)):
+            keep = arr[idx]
+            arr[idx] = keep + h
+            up = bo.binocular_loss(shifted, depth, gt, f, td)
+            arr[idx] = keep - h
+            dn = bo.binocular_loss(shifted, depth, gt, f, td)
+            arr[idx] = keep
+            assert abs((up - dn) / (2 * h) - grad[idx]) < 1e-6 * max(1.0, np.abs(grad).max() * 1e3)
+
+
+def test_api_surface_and_loud_failures():
+    import inspect
+    from binocular3dgs_b200 import binocular
+    assert list(inspect.signature(binocular.inverse_warp_images).parameters) == [
+        "image", "disparity", "row_indices", "column_indices"]
+    assert list(inspect.signature(binocular.SmoothLoss.forward).parameters) == ["self", "disparity", "image"]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        binocular.inverse_warp_images(torch.zeros(1, 3, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        binocular.binocular_consistency_loss(torch.zeros(3, 8, 8), torch.zeros(1, 8, 8), torch.zeros(3, 8, 8), 1.0, 0.1)
+    with pytest.raises(RuntimeError):
+        binocular.inverse_warp_images(torch.zeros(3, 8, 8), torch.zeros(1, 8, 8))
+    with pytest.raises(RuntimeError, match="H, W >= 3"):
+        binocular.binocular_consistency_loss(torch.zeros(3, 2, 8), torch.zeros(1, 2, 8), torch.zeros(3, 2, 8), 1.0, 0.1)
+
+
+# ------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_loss_matches_reference_golden(name):
+    from binocular3dgs_b200 import binocular
+    c, g, (shifted, depth, gt) = load(name)
+    a = shifted.cuda().requires_grad_(True)
+    d = depth.cuda().requires_grad_(True)
+    v = binocular.binocular_consistency_loss(a, d, gt.cuda(), c["focal_x"], c["trans_dist"])
+    v.backward()
+    assert abs(float(v.detach()) - float(g["loss"])) < VAL_TOL
+    assert rel(a.grad.cpu().numpy(), g["grad_shifted"]) < GRAD_TOL
+    assert rel(d.grad.cpu().numpy(), g["grad_depth"]) < GRAD_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_standalone_operators_match_reference_golden(name):
+    """train.py:128-136 statement by statement on the drop-in operators."""
+    from binocular3dgs_b200 import binocular
+    from binocular3dgs_b200.losses import l1_loss
+    c, g, (shifted, depth, gt) = load(name)
+    H, W = depth.shape[-2:]
+    rows = torch.arange(0, H).view(-1, 1).repeat(1, W).cuda()
+    cols = torch.arange(0, W).repeat(H, 1).cuda()
+    mask = torch.ones((1, H, W), dtype=torch.float32).cuda()
+    a = shifted.cuda().requires_grad_(True)
+    d = depth.cuda().requires_grad_(True)
+    gt = gt.cuda()
+    smooth_loss = binocular.SmoothLoss()
+    disparity = c["focal_x"] * (-c["trans_dist"]) / (d + 1e-5)
+    warped = binocular.inverse_warp_images(a.unsqueeze(0), disparity.unsqueeze(0), rows, cols)
+    shift_mask = binocular.inverse_warp_images(mask.unsqueeze(0), disparity.unsqueeze(0), rows, cols)
+    loss = (l1_loss(warped, gt.unsqueeze(0), mask=shift_mask) +
+            0.05 * smooth_loss.forward(disparity=disparity * shift_mask, image=gt.unsqueeze(0)))
+    loss.backward()
+    assert np.abs(warped.detach().cpu().numpy()[0] - g["warped"]).max() < WARP_TOL
+    assert np.abs(shift_mask.detach().cpu().numpy()[0, 0] - g["shift_mask"]).max() < WARP_TOL
+    assert abs(float(loss.detach()) - float(g["loss"])) < VAL_TOL
+    assert rel(a.grad.cpu().numpy(), g["grad_shifted"]) < GRAD_TOL
+    assert rel(d.grad.cpu().numpy(), g["grad_depth"]) < GRAD_TOL
+    # dense upstream gradient through the warp alone
+    a2 = shifted.cuda().requires_grad_(True)
+    d2 = disparity.detach().clone().requires_grad_(True)
+    w2 = binocular.inverse_warp_images(a2.unsqueeze(0), d2.unsqueeze(0), rows, cols)
+    w2.backward(torch.from_numpy(g["warp_up"]).cuda().unsqueeze(0))
+    assert rel(a2.grad.cpu().numpy(), g["warp_grad_image"]) < GRAD_TOL
+    assert rel(d2.grad.cpu().numpy(), g["warp_grad_disparity"]) < GRAD_TOL
+
+
+@pytest.mark.gpu
+def test_fused_loss_full_size_vs_oracle():
+    """LLFF size (1008x756), ragged against the 32x8 block, non-unit upstream gradient."""
+    from binocular3dgs_b200 import binocular
+    c = dict(H=756, W=1008, seed=31, focal_x=815.0, trans_dist=0.27, depth_lo=0.0, depth_hi=9.0)
+    shifted, depth, gt = mbg.make_inputs(**c)
+    a = shifted.cuda().requires_grad_(True)
+    d = depth.cuda().requires_grad_(True)
+    v = binocular.binocular_consistency_loss(a, d, gt.cuda(), c["focal_x"], c["trans_dist"])
+    (3.0 * v).backward()
+    s, dd, t = shifted.numpy(), depth.numpy()[0], gt.numpy()
+    assert abs(float(v.detach()) - bo.binocular_loss(s, dd, t, c["focal_x"], c["trans_dist"])) < VAL_TOL
+    gi, gd = bo.binocular_loss_grad(s, dd, t, c["focal_x"], c["trans_dist"])
+    assert rel(a.grad.cpu().numpy(), 3.0 * gi) < GRAD_TOL
+    # pixels whose disparity sits within float32 rounding of an integer may take the other
+    # (equally valid) tap pair: compare away from them
+    disp = bo.disparity_of(dd, c["focal_x"], c["trans_dist"])
+    safe = np.abs(disp - np.round(disp)) > 1e-3 * np.maximum(1.0, np.abs(disp))
+    got = d.grad.cpu().numpy()[0]
+    assert np.abs((got - 3.0 * gd) * safe).max() / np.abs(gd).max() < GRAD_TOL * 3.0
