@@ -387,6 +387,11 @@ def main():
             next_rows["binocular_loss"] = bench_loss.measure_binocular(dev)
         except Exception as ex:
             next_rows["binocular_loss"] = {"error": repr(ex)}
+        try:  # §8(f) rank 3 at the bench's own P and M
+            import bench_params
+            next_rows["parameter_plumbing"] = bench_params.measure(dev, P, M)
+        except Exception as ex:
+            next_rows["parameter_plumbing"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

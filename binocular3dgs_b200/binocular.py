@@ -26,11 +26,11 @@ def _fns():
     if _lib is None:
         lib = _backend.native().lib
         for name, args in (("b3gs_binocular_forward", [_I, _I, _V, _V, _V, _F, _V, _V]),
-                           ("b3gs_binocular_backward", [_I, _I, _V, _V, _V, _F, _V, _V, _V, _V]),
+                           ("b3gs_binocular_backward", [_I, _I, _V, _V, _V, _F, _V, _F, _F, _V, _V, _V]),
                            ("b3gs_warp_forward", [_I, _I, _I, _V, _V, _V, _V]),
                            ("b3gs_warp_backward", [_I, _I, _I, _V, _V, _V, _V, _V, _V]),
                            ("b3gs_smooth_forward", [_I, _I, _V, _V, _V, _V]),
-                           ("b3gs_smooth_backward", [_I, _I, _V, _V, _V, _V, _V])):
+                           ("b3gs_smooth_backward", [_I, _I, _V, _V, _V, _F, _V, _V])):
             fn = getattr(lib, name)
             fn.argtypes, fn.restype = args, _I
         _lib = lib
@@ -123,10 +123,10 @@ class _Smooth(torch.autograd.Function):
         H, W = disparity.shape[-2:]
         dev = disparity.device
         with torch.cuda.device(dev):
-            scale = (g.reshape(1).to(torch.float32) / float((H - 2) * (W - 2))).contiguous()
+            up = g.reshape(1).to(torch.float32).contiguous()
             out = torch.empty_like(disparity)
-            _call(_fns().b3gs_smooth_backward, H, W, disparity.data_ptr(), image.data_ptr(), scale.data_ptr(),
-                  out.data_ptr(), _stream(dev))
+            _call(_fns().b3gs_smooth_backward, H, W, disparity.data_ptr(), image.data_ptr(), up.data_ptr(),
+                  1.0 / float((H - 2) * (W - 2)), out.data_ptr(), _stream(dev))
         return out, None
 
 
@@ -169,11 +169,11 @@ class _Binocular(torch.autograd.Function):
         H, W, k_disp, k_l1, k_sm = ctx.meta
         dev = depth.device
         with torch.cuda.device(dev):
-            scales = (g.reshape(1).to(torch.float32) * torch.tensor([k_l1, k_sm], device=dev)).contiguous()
+            up = g.reshape(1).to(torch.float32).contiguous()
             g_shifted = torch.empty_like(shifted)
             g_depth = torch.empty_like(depth)
             _call(_fns().b3gs_binocular_backward, H, W, shifted.data_ptr(), depth.data_ptr(), gt.data_ptr(), k_disp,
-                  scales.data_ptr(), g_shifted.data_ptr(), g_depth.data_ptr(), _stream(dev))
+                  up.data_ptr(), k_l1, k_sm, g_shifted.data_ptr(), g_depth.data_ptr(), _stream(dev))
         return g_shifted, g_depth, None, None, None
 
 

@@ -220,13 +220,14 @@ __device__ __forceinline__ void red_pair(float* __restrict__ row, bool valid, in
 __global__ void __launch_bounds__(kThreads) binocular_backward_kernel(int H, int W, const float* __restrict__ shifted,
                                                                      const float* __restrict__ depth,
                                                                      const float* __restrict__ gt, float k_disp,
-                                                                     const float* __restrict__ scales,
+                                                                     const float* __restrict__ upstream, float k_l1,
+                                                                     float k_sm,
                                                                      float* __restrict__ dL_dshifted,
                                                                      float* __restrict__ dL_ddepth) {
     const float g_dm = smooth_backward_term<true>(depth, k_disp, gt, W, H);
     const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
     const bool in = x < W && y < H;
-    const float g_l1 = scales[0], g_sm = scales[1];
+    const float g_l1 = upstream[0] * k_l1, g_sm = upstream[0] * k_sm;
     const size_t plane = (size_t)H * W, row = (size_t)(in ? y : 0) * W;
     float dep = 0.f, disp = 0.f, g_disp = 0.f;
     Taps t;
@@ -315,11 +316,11 @@ __global__ void __launch_bounds__(kThreads) smooth_forward_kernel(int H, int W, 
 
 __global__ void __launch_bounds__(kThreads) smooth_backward_kernel(int H, int W, const float* __restrict__ disparity,
                                                                   const float* __restrict__ image,
-                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ upstream, float k,
                                                                   float* __restrict__ dL_ddisparity) {
     const float g = smooth_backward_term<false>(disparity, 0.f, image, W, H);
     const int x = blockIdx.x * kBX + threadIdx.x, y = blockIdx.y * kBY + threadIdx.y;
-    if (x < W && y < H) dL_ddisparity[(size_t)y * W + x] = scale[0] * g;
+    if (x < W && y < H) dL_ddisparity[(size_t)y * W + x] = upstream[0] * k * g;
 }
 
 static dim3 tile_grid(int W, int H) { return dim3((W + kBX - 1) / kBX, (H + kBY - 1) / kBY); }
@@ -341,11 +342,13 @@ int b3gs_binocular_forward(int H, int W, const float* shifted, const float* dept
 }
 
 int b3gs_binocular_backward(int H, int W, const float* shifted, const float* depth, const float* gt, float k_disp,
-                            const float* scales, float* dL_dshifted, float* dL_ddepth, void* stream) {
-    if (H < 3 || W < 3 || !shifted || !depth || !gt || !scales || !dL_dshifted || !dL_ddepth) return -1;
+                            const float* upstream, float k_l1, float k_sm, float* dL_dshifted, float* dL_ddepth,
+                            void* stream) {
+    if (H < 3 || W < 3 || !shifted || !depth || !gt || !upstream || !dL_dshifted || !dL_ddepth) return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(dL_dshifted, 0, 3 * sizeof(float) * (size_t)H * W, st) != cudaSuccess) return -2;
-    binocular_backward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, shifted, depth, gt, k_disp, scales,
+    binocular_backward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, shifted, depth, gt, k_disp, upstream,
+                                                                         k_l1, k_sm,
                                                                          dL_dshifted, dL_ddepth);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -379,11 +382,12 @@ int b3gs_smooth_forward(int H, int W, const float* disparity, const float* image
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int b3gs_smooth_backward(int H, int W, const float* disparity, const float* image, const float* scale,
+int b3gs_smooth_backward(int H, int W, const float* disparity, const float* image, const float* upstream, float k,
                          float* dL_ddisparity, void* stream) {
-    if (H < 3 || W < 3 || !disparity || !image || !scale || !dL_ddisparity) return -1;
+    if (H < 3 || W < 3 || !disparity || !image || !upstream || !dL_ddisparity) return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    smooth_backward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, disparity, image, scale, dL_ddisparity);
+    smooth_backward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, disparity, image, upstream, k,
+                                                                      dL_ddisparity);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

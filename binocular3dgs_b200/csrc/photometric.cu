@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) photometric_backward_kernel(int H, int W,
                                                                   const float* __restrict__ dm_dmu1,
                                                                   const float* __restrict__ dm_dsigma1,
                                                                   const float* __restrict__ dm_dsigma12,
-                                                                  const float* __restrict__ scales /* [0] gS, [1] gL1 */,
+                                                                  const float* __restrict__ upstream /* device float[1] */, float k_ssim,
+                                                                  float k_l1,
                                                                   float* __restrict__ dL_dimg1) {
     __shared__ float s[3][kExt][kExt + 1];
     __shared__ float h[3][kExt][kTile + 1];
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) photometric_backward_kernel(int H, int W,
     }
     const size_t o = c * plane + (size_t)gy * W + gx;
     const float x = img1[o], y = img2[o];
-    const float gS = scales[0], gL1 = scales[1];
+    const float g = upstream[0], gS = g * k_ssim, gL1 = g * k_l1;
     const float diff = x - y;
     const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
     dL_dimg1[o] = gS * (a + 2.f * x * b + y * d) + gL1 * sgn;
@@ -202,14 +203,16 @@ int b3gs_photometric_forward(int C, int H, int W, const float* img1, const float
 }
 
 int b3gs_photometric_backward(int C, int H, int W, const float* img1, const float* img2, const float* dm_dmu1,
-                              const float* dm_dsigma1_sq, const float* dm_dsigma12, const float* scales,
+                              const float* dm_dsigma1_sq, const float* dm_dsigma12, const float* upstream,
+                              float k_ssim, float k_l1,
                               float* dL_dimg1, void* stream) {
-    if (C <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !scales ||
+    if (C <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !upstream ||
         !dL_dimg1)
         return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, C), block(kTile, kTile);
-    photometric_backward_kernel<<<grid, block, 0, st>>>(H, W, img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, scales,
+    photometric_backward_kernel<<<grid, block, 0, st>>>(H, W, img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, upstream,
+                                                       k_ssim, k_l1,
                                                        dL_dimg1);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -27,7 +27,7 @@ def _fns():
         lib = _backend.native().lib
         lib.b3gs_photometric_forward.argtypes = [ctypes.c_int] * 3 + [_V] * 8
         lib.b3gs_photometric_forward.restype = ctypes.c_int
-        lib.b3gs_photometric_backward.argtypes = [ctypes.c_int] * 3 + [_V] * 8
+        lib.b3gs_photometric_backward.argtypes = [ctypes.c_int] * 3 + [_V] * 6 + [ctypes.c_float] * 2 + [_V] * 2
         lib.b3gs_photometric_backward.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -75,10 +75,10 @@ class _Photometric(torch.autograd.Function):
         C, H, W, ks, kl, shape = ctx.meta
         dev = a.device
         with torch.cuda.device(dev):
-            scales = (grad_out.reshape(1).to(torch.float32) * torch.tensor([ks, kl], device=dev)).contiguous()
+            up = grad_out.reshape(1).to(torch.float32).contiguous()
             grad = torch.empty((C, H, W), dtype=torch.float32, device=dev)
             rc = _fns().b3gs_photometric_backward(C, H, W, a.data_ptr(), b.data_ptr(), maps[0].data_ptr(),
-                                                  maps[1].data_ptr(), maps[2].data_ptr(), scales.data_ptr(),
+                                                  maps[1].data_ptr(), maps[2].data_ptr(), up.data_ptr(), ks, kl,
                                                   grad.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"b3gs_photometric_backward failed ({rc})")

@@ -221,17 +221,18 @@ B3GS_API int b3gs_profile_read(double* ms_total, unsigned long long* calls, int 
  * map (w.r.t. mu1, E[x^2], E[xy]) needed by the backward, optionally the SSIM map itself
  * (NULL to skip), and sums[0] = sum of the SSIM map, sums[1] = sum |img1 - img2| (device
  * doubles, zeroed by the call).
- * b3gs_photometric_backward writes dL/dimg1 = scales[0] * dSSIMsum/dimg1 +
- * scales[1] * sign(img1 - img2); scales is a DEVICE float[2] so the upstream gradient
- * never has to visit the host (for the combined loss: scales = {-lambda*g/(CHW),
- * (1-lambda)*g/(CHW)}).  Gradient flows to img1 only.
+ * b3gs_photometric_backward writes dL/dimg1 = g * (k_ssim * dSSIMsum/dimg1 +
+ * k_l1 * sign(img1 - img2)) with g = upstream[0], a DEVICE float so the upstream gradient
+ * never has to visit the host (for the combined loss: k_ssim = -lambda/(CHW),
+ * k_l1 = (1-lambda)/(CHW)).  Gradient flows to img1 only.
  */
 B3GS_API int b3gs_photometric_forward(int C, int H, int W, const float* img1, const float* img2, float* dm_dmu1,
                                       float* dm_dsigma1_sq, float* dm_dsigma12, float* ssim_map, double* sums,
                                       void* stream);
 B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, const float* img2,
                                        const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
-                                       const float* scales, float* dL_dimg1, void* stream);
+                                       const float* upstream, float k_ssim, float k_l1, float* dL_dimg1,
+                                       void* stream);
 
 /*
  * ---- binocular-consistency loss -------------------------------
@@ -248,14 +249,14 @@ B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, c
  * smoothness terms; the caller forms loss = sums[0]/(3HW) + w*(sums[1]+sums[2])/((H-2)(W-2)).
  * b3gs_binocular_backward recomputes from the same inputs (nothing is saved) and writes
  * dL/dshifted (zeroed by the call, accumulated with float REDs) and dL/ddepth;
- * scales is a DEVICE float[2] = {g/(3HW), g*w/((H-2)(W-2))} so the upstream gradient g
- * never visits the host.  Gradient flows to `shifted` and `depth` only.
+ * upstream is a DEVICE float[1] holding the upstream gradient g (it never visits the
+ * host); k_l1 = 1/(3HW) and k_sm = w/((H-2)(W-2)) scale the two terms.  Gradient flows to `shifted` and `depth` only.
  */
 B3GS_API int b3gs_binocular_forward(int H, int W, const float* shifted, const float* depth, const float* gt,
                                     float k_disp, double* sums, void* stream);
 B3GS_API int b3gs_binocular_backward(int H, int W, const float* shifted, const float* depth, const float* gt,
-                                     float k_disp, const float* scales, float* dL_dshifted, float* dL_ddepth,
-                                     void* stream);
+                                     float k_disp, const float* upstream, float k_l1, float k_sm, float* dL_dshifted,
+                                     float* dL_ddepth, void* stream);
 
 /* The constituents as stand-alone operators (drop-in for the reference's Python API).
  * b3gs_warp_*: inverse_warp_images for one image float[C,H,W] and one disparity map
@@ -263,16 +264,62 @@ B3GS_API int b3gs_binocular_backward(int H, int W, const float* shifted, const f
  * accumulates into it; dL_ddisparity may be NULL.
  * b3gs_smooth_*: SmoothLoss.forward(disparity float[H,W], image float[3,H,W])
  * (utils/loss_utils.py:68-91): sums[2] (device doubles, zeroed by the call) = x / y sums
- * over (H-2)(W-2); the backward writes dL/ddisparity = scale[0] * d(sums[0]+sums[1])/
- * d(disparity) with scale a DEVICE float[1]. */
+ * over (H-2)(W-2); the backward writes dL/ddisparity = upstream[0] * k *
+ * d(sums[0]+sums[1])/d(disparity) with upstream a DEVICE float[1]. */
 B3GS_API int b3gs_warp_forward(int C, int H, int W, const float* image, const float* disparity, float* warped,
                                void* stream);
 B3GS_API int b3gs_warp_backward(int C, int H, int W, const float* image, const float* disparity,
                                 const float* dL_dwarped, float* dL_dimage, float* dL_ddisparity, void* stream);
 B3GS_API int b3gs_smooth_forward(int H, int W, const float* disparity, const float* image, double* sums,
                                  void* stream);
-B3GS_API int b3gs_smooth_backward(int H, int W, const float* disparity, const float* image, const float* scale,
-                                  float* dL_ddisparity, void* stream);
+B3GS_API int b3gs_smooth_backward(int H, int W, const float* disparity, const float* image, const float* upstream,
+                                  float k, float* dL_ddisparity, void* stream);
+
+/*
+ * ---- per-step parameter plumbing ------------------------------
+ * The elementwise work scene/gaussian_model.py runs around the rasterizer every
+ * iteration, one streaming kernel each.
+ *
+ * b3gs_activate_forward: raw parameters -> rasterizer inputs (gaussian_model.py:95-115):
+ *   shs[P,M,3] = cat(f_dc[P,1,3], f_rest[P,M-1,3]); opacities = sigmoid(opacity_raw[P]);
+ *   scales = exp(scaling_raw[P,3]); rotations = normalize(rotation_raw[P,4]) (eps 1e-12).
+ * b3gs_activate_backward: the duals, recomputed from the raw parameters; any g_* input
+ *   may be NULL (that attribute received no gradient), its output is then left untouched.
+ * b3gs_adam_multi: torch.optim.Adam's update (gaussian_model.py:154-163: lr per group,
+ *   betas (0.9, 0.999), eps 1e-15, no weight decay / amsgrad) for up to
+ *   B3GS_ADAM_MAX_TENSORS tensors in ONE launch.  step_size = lr / (1 - beta1^t) and
+ *   inv_bias_correction2_sqrt = 1 / sqrt(1 - beta2^t) are formed by the caller in double,
+ *   as torch does.  Updates param, exp_avg, exp_avg_sq in place.
+ * b3gs_opacity_decay: opacity_raw <- logit(sigmoid(opacity_raw) * factor)
+ *   (gaussian_model.py:307-309).
+ * b3gs_densify_stats: for Gaussians with radii > 0 (train.py:170-171,
+ *   gaussian_model.py:409-411): xyz_gradient_accum += ||viewspace_grad[:, :2]||,
+ *   denom += 1, max_radii2D = max(max_radii2D, radii) (max_radii2D may be NULL).
+ *   viewspace_grad is float[P,3] (the rasterizer's dL/dmeans2D).
+ */
+#define B3GS_ADAM_MAX_TENSORS 8
+typedef struct B3gsAdamTensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    size_t n;
+    float step_size;
+    float inv_bias_correction2_sqrt;
+} B3gsAdamTensor;
+
+B3GS_API int b3gs_activate_forward(int P, int M, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                                   const float* scaling_raw, const float* rotation_raw, float* shs, float* opacities,
+                                   float* scales, float* rotations, void* stream);
+B3GS_API int b3gs_activate_backward(int P, int M, const float* opacity_raw, const float* scaling_raw,
+                                    const float* rotation_raw, const float* g_shs, const float* g_opacities,
+                                    const float* g_scales, const float* g_rotations, float* g_f_dc, float* g_f_rest,
+                                    float* g_opacity_raw, float* g_scaling_raw, float* g_rotation_raw, void* stream);
+B3GS_API int b3gs_adam_multi(int n_tensors, const B3gsAdamTensor* tensors, double beta1, double beta2, double eps,
+                             void* stream);
+B3GS_API int b3gs_opacity_decay(int P, float factor, float* opacity_raw, void* stream);
+B3GS_API int b3gs_densify_stats(int P, const float* viewspace_grad, const int* radii, float* xyz_gradient_accum,
+                                float* denom, float* max_radii2D, void* stream);
 
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
