@@ -352,6 +352,37 @@ static void radix_pass(const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_
 
 static size_t radix_scratch_elems(int n) { return (size_t)kRadixBins * radix_blocks(n) + kRadixBins; }
 
+// ------------------------------------------------------------------ generic (key, iota) sort
+// Stable LSD sort of n 32-bit keys on bits [0, bits) carrying the original index: the
+// Morton-order pass of the k-nearest-neighbour initialiser (knn.cu) reuses the rasterizer's
+// radix passes.  scratch: keysA keysB idsA idsB (n words each) + histograms.
+size_t sort_keys_iota_scratch_bytes(int n) {
+    return 4 * align_up((size_t)n * 4, 256) + align_up(radix_scratch_elems(n) * 4, 256);
+}
+
+cudaError_t sort_keys_iota_u32(int n, const uint32_t* keys, int bits, char* scratch, const uint32_t** keys_sorted,
+                               const uint32_t** ids_sorted, cudaStream_t stream) {
+    char* q = scratch;
+    uint32_t* kbuf[2]; uint32_t* ibuf[2];
+    kbuf[0] = reinterpret_cast<uint32_t*>(q); q += align_up((size_t)n * 4, 256);
+    kbuf[1] = reinterpret_cast<uint32_t*>(q); q += align_up((size_t)n * 4, 256);
+    ibuf[0] = reinterpret_cast<uint32_t*>(q); q += align_up((size_t)n * 4, 256);
+    ibuf[1] = reinterpret_cast<uint32_t*>(q); q += align_up((size_t)n * 4, 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(q);
+    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(n);
+    const int passes = bits <= 0 ? 1 : (bits + 7) / 8;
+    const uint32_t* kin = keys;
+    const uint32_t* iin = nullptr;
+    for (int p = 0; p < passes; p++) {
+        radix_pass<uint32_t>(kin, iin, kbuf[p & 1], ibuf[p & 1], hist, totals, n, 8 * p, p == 0, stream);
+        kin = kbuf[p & 1];
+        iin = ibuf[p & 1];
+    }
+    *keys_sorted = kin;
+    *ids_sorted = iin;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ phase 1 (P-sized)
 // The whole of phase 1 — four radix passes over float_bits(depth) and the gather-scan of
 // tiles_touched in the resulting order — as ONE cooperative kernel: the P-sized passes

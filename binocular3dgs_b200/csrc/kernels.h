@@ -67,6 +67,12 @@ struct BinningPhase2Args {
 size_t binning_phase2_scratch_bytes(int R);
 cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream);
 
+// Stable LSD radix sort of n (key, original index) pairs on key bits [0, bits); returns
+// pointers (inside scratch) to the sorted keys and the permutation.
+size_t sort_keys_iota_scratch_bytes(int n);
+cudaError_t sort_keys_iota_u32(int n, const uint32_t* keys, int bits, char* scratch, const uint32_t** keys_sorted,
+                               const uint32_t** ids_sorted, cudaStream_t stream);
+
 // ---------------------------------------------------------------- K6 / K7
 struct CompositeFwdArgs {
     int W, H, grid_x, grid_y;

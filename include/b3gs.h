@@ -321,6 +321,21 @@ B3GS_API int b3gs_opacity_decay(int P, float factor, float* opacity_raw, void* s
 B3GS_API int b3gs_densify_stats(int P, const float* viewspace_grad, const int* radii, float* xyz_gradient_accum,
                                 float* denom, float* max_radii2D, void* stream);
 
+/*
+ * ---- simple-knn distCUDA2 -------------------------------------
+ * mean_dist2[i] = mean of the squared distances from point i to its 3 nearest neighbours
+ * (submodules/simple-knn/simple_knn.cu:185-221 SimpleKNN::knn, bound as
+ * simple_knn._C.distCUDA2 in spatial.cu:15-25; used at scene/gaussian_model.py:134).
+ * points: float[P,3]; mean_dist2: float[P].  Exact search, distances evaluated with the
+ * reference's expression, so results are bit-identical to the reference's.  With fewer
+ * than 3 other points the missing neighbours count as FLT_MAX (the result overflows to
+ * inf), as in the reference.  scratch: device memory of at least
+ * b3gs_dist_cuda2_scratch_bytes(P) bytes; no allocation, no host synchronisation.
+ */
+B3GS_API size_t b3gs_dist_cuda2_scratch_bytes(int P);
+B3GS_API int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,
+                             void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
 
