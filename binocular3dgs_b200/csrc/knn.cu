@@ -5,7 +5,8 @@
 // The result is an exact geometric quantity — (d1^2 + d2^2 + d3^2) / 3 over the true three
 // nearest neighbours — so any exact search reproduces the reference bit for bit as long as
 // the distance expression is evaluated the way its SASS does:
-//     d = neighbour - query;  dist = fma(d.z, d.z, fma(d.y, d.y, d.x * d.x));
+//     d = neighbour - query;  dist = fma(d.z, d.z, fma(d.x, d.x, d.y * d.y));   (the MIDDLE
+//     product is rounded alone — the same contraction as common.cuh dot3)
 //     out = ((best0 + best1) + best2) / 3.0f   (IEEE division)
 // Missing neighbours (P < 4) stay at FLT_MAX as in the reference (the sum overflows to inf).
 //
@@ -84,29 +85,42 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x) {  // 10 bits -> every 
     return x;
 }
 
-// 30-bit Morton code of each point inside the cloud's bounding box (simple_knn.cu:46-73)
+// 60-bit Morton code (20 bits per axis) of each point inside the cloud's bounding box, as
+// two 30-bit halves.  The reference uses 10 bits per axis (simple_knn.cu:46-73); with SfM
+// clouds a few far outliers stretch the box and whole dense clusters collapse into a handful
+// of 10-bit cells, inside which the order — and so the leaves — would be arbitrary.
 __global__ void __launch_bounds__(256) knn_morton_kernel(int P, const float* __restrict__ points,
                                                         const uint32_t* __restrict__ bounds,
-                                                        uint32_t* __restrict__ codes) {
+                                                        uint32_t* __restrict__ codes_lo,
+                                                        uint32_t* __restrict__ codes_hi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    uint32_t code = 0;
+    uint32_t lo30 = 0, hi30 = 0;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float lo = ord2f(bounds[c]), hi = ord2f(bounds[3 + c]);
         const float ext = hi - lo;
         const float t = ext > 0.f ? (points[3 * (size_t)i + c] - lo) / ext : 0.f;
-        const uint32_t q = (uint32_t)fminf(fmaxf(t * 1023.f, 0.f), 1023.f);
-        code |= spread10(q) << c;
+        const uint32_t q = (uint32_t)fminf(fmaxf(t * 1048575.f, 0.f), 1048575.f);
+        lo30 |= spread10(q & 1023u) << c;
+        hi30 |= spread10(q >> 10) << c;
     }
-    codes[i] = code;
+    codes_lo[i] = lo30;
+    codes_hi[i] = hi30;
+}
+
+__global__ void __launch_bounds__(256) knn_gather_kernel(int P, const uint32_t* __restrict__ src,
+                                                        const uint32_t* __restrict__ idx, uint32_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) dst[i] = src[idx[i]];
 }
 
 // One block = one super box of 1024 Morton-consecutive points = 32 leaves (one per warp).
 // Gathers the points into Morton order (float4: xyz + original index bits) and reduces the
 // leaf and super boxes.  Positions >= P are padded with +inf points and neutral boxes.
 __global__ void __launch_bounds__(kSuper) knn_leaf_kernel(int P, const float* __restrict__ points,
-                                                         const uint32_t* __restrict__ ids_sorted,
+                                                         const uint32_t* __restrict__ ids_by_lo,
+                                                         const uint32_t* __restrict__ perm_by_hi,
                                                          float4* __restrict__ sorted_pts,
                                                          KnnBox* __restrict__ leaf_boxes,
                                                          KnnBox* __restrict__ super_boxes) {
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(kSuper) knn_leaf_kernel(int P, const float* __
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     float4 p = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
     if (pos < P) {
-        const uint32_t id = ids_sorted[pos];
+        const uint32_t id = ids_by_lo[perm_by_hi[pos]];  // LSD: low half first, then stable by high half
         p = make_float4(points[3 * (size_t)id], points[3 * (size_t)id + 1], points[3 * (size_t)id + 2],
                         __uint_as_float(id));
         lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z;
@@ -173,7 +187,7 @@ __device__ __forceinline__ float box_box_dist2(const KnnBox& a, const KnnBox& q)
 __device__ __forceinline__ void update3(float qx, float qy, float qz, float px, float py, float pz, float& b0, float& b1,
                                         float& b2) {
     const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
-    float dist = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     if (b0 > dist) { const float t = b0; b0 = dist; dist = t; }
     if (b1 > dist) { const float t = b1; b1 = dist; dist = t; }
     if (b2 > dist) { b2 = dist; }
@@ -241,8 +255,14 @@ __global__ void __launch_bounds__(kSearchWarps * 32) knn_search_kernel(int P, in
             while (m2) {
                 const int l = s * 32 + __ffs(m2) - 1;
                 m2 &= m2 - 1;
-                // the bound may have tightened since the ballot
-                if (box_box_dist2(leaf_boxes[l], qbox) > bound) continue;  // warp-uniform
+                // exact per-query test (simple_knn.cu:118-130 distBoxPoint) against each lane's
+                // own current 3rd-best: scan only if some query can still improve
+                const KnnBox lb = leaf_boxes[l];
+                const float gx = fmaxf(fmaxf(lb.lo.x - q.x, q.x - lb.hi.x), 0.f);
+                const float gy = fmaxf(fmaxf(lb.lo.y - q.y, q.y - lb.hi.y), 0.f);
+                const float gz = fmaxf(fmaxf(lb.lo.z - q.z, q.z - lb.hi.z), 0.f);
+                const bool want = valid && (gx * gx + gy * gy + gz * gz) * 0.999999f <= b2;
+                if (!__any_sync(0xffffffffu, want)) continue;
                 sp[lane] = sorted_pts[l * kLeaf + lane];
                 __syncwarp();
 #pragma unroll 8
@@ -267,7 +287,7 @@ extern "C" {
 size_t b3gs_dist_cuda2_scratch_bytes(int P) {
     if (P <= 0) return 256;
     const size_t n_super = ((size_t)P + kSuper - 1) / kSuper;
-    return knn_align(6 * 4) + knn_align((size_t)P * 4) + knn_align(sort_keys_iota_scratch_bytes(P)) +
+    return knn_align(6 * 4) + 3 * knn_align((size_t)P * 4) + 2 * knn_align(sort_keys_iota_scratch_bytes(P)) +
            knn_align(n_super * kSuper * sizeof(float4)) + knn_align(n_super * 32 * sizeof(KnnBox)) +
            knn_align(n_super * sizeof(KnnBox));
 }
@@ -280,8 +300,11 @@ int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void* scratch
     const int n_super = (P + kSuper - 1) / kSuper, n_leaves = (P + kLeaf - 1) / kLeaf;
     char* q = reinterpret_cast<char*>(scratch);
     uint32_t* bounds = reinterpret_cast<uint32_t*>(q); q += knn_align(6 * 4);
-    uint32_t* codes = reinterpret_cast<uint32_t*>(q);  q += knn_align((size_t)P * 4);
-    char* sort_scratch = q;                            q += knn_align(sort_keys_iota_scratch_bytes(P));
+    uint32_t* codes_lo = reinterpret_cast<uint32_t*>(q); q += knn_align((size_t)P * 4);
+    uint32_t* codes_hi = reinterpret_cast<uint32_t*>(q); q += knn_align((size_t)P * 4);
+    uint32_t* hi_by_lo = reinterpret_cast<uint32_t*>(q); q += knn_align((size_t)P * 4);
+    char* sort_scratch1 = q;                           q += knn_align(sort_keys_iota_scratch_bytes(P));
+    char* sort_scratch2 = q;                           q += knn_align(sort_keys_iota_scratch_bytes(P));
     float4* sorted_pts = reinterpret_cast<float4*>(q); q += knn_align((size_t)n_super * kSuper * sizeof(float4));
     KnnBox* leaf_boxes = reinterpret_cast<KnnBox*>(q); q += knn_align((size_t)n_super * 32 * sizeof(KnnBox));
     KnnBox* super_boxes = reinterpret_cast<KnnBox*>(q);
@@ -291,11 +314,14 @@ int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void* scratch
     int gb = (P + 255) / 256;
     if (gb > 148 * 8) gb = 148 * 8;
     knn_bounds_kernel<<<gb, 256, 0, st>>>(P, points, bounds);
-    knn_morton_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, points, bounds, codes);
+    knn_morton_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, points, bounds, codes_lo, codes_hi);
     count_launch(2);
-    const uint32_t *codes_sorted = nullptr, *ids_sorted = nullptr;
-    if (sort_keys_iota_u32(P, codes, 30, sort_scratch, &codes_sorted, &ids_sorted, st) != cudaSuccess) return -2;
-    knn_leaf_kernel<<<n_super, kSuper, 0, st>>>(P, points, ids_sorted, sorted_pts, leaf_boxes, super_boxes);
+    const uint32_t *keys_sorted = nullptr, *ids_by_lo = nullptr, *perm_by_hi = nullptr;
+    if (sort_keys_iota_u32(P, codes_lo, 30, sort_scratch1, &keys_sorted, &ids_by_lo, st) != cudaSuccess) return -2;
+    knn_gather_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, codes_hi, ids_by_lo, hi_by_lo);
+    if (sort_keys_iota_u32(P, hi_by_lo, 30, sort_scratch2, &keys_sorted, &perm_by_hi, st) != cudaSuccess) return -2;
+    knn_leaf_kernel<<<n_super, kSuper, 0, st>>>(P, points, ids_by_lo, perm_by_hi, sorted_pts, leaf_boxes, super_boxes);
+    count_launch();
     knn_search_kernel<<<(n_leaves + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(
         P, n_leaves, n_super, sorted_pts, leaf_boxes, super_boxes, mean_dist2);
     count_launch(2);

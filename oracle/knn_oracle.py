@@ -3,9 +3,9 @@
 
 The reference's Morton boxes only prune the search; what it returns for every point is the
 mean of the squared distances to its 3 exact nearest neighbours, each evaluated in float32 as
-    d = neighbour - query;  dist = fma(d.z, d.z, fma(d.y, d.y, d.x * d.x))
-(the contraction nvcc emits for `d.x*d.x + d.y*d.y + d.z*d.z`, read from the SASS of the
-reference compiled for sm_100a) and combined as ((b0 + b1) + b2) / 3.0f, with FLT_MAX for
+    d = neighbour - query;  dist = fma(d.z, d.z, fma(d.x, d.x, d.y * d.y))
+(the contraction nvcc emits for `d.x*d.x + d.y*d.y + d.z*d.z` — the middle product is
+rounded alone — read from the SASS of the reference compiled for sm_100a) and combined as ((b0 + b1) + b2) / 3.0f, with FLT_MAX for
 missing neighbours when P < 4.  Here: candidates from a float64 k-d tree (scipy), the
 float32 expression emulated through float64 (products of two float32 are exact in float64;
 the fused add is rounded once to float64 and once to float32 — double rounding can differ
@@ -25,8 +25,8 @@ def _fma32(a, b, c):
 def _dist32(q, p):
     """q (..., 3), p (..., 3) float32 -> float32 squared distance, reference expression."""
     d = (p - q).astype(np.float32)
-    t = (d[..., 0] * d[..., 0]).astype(np.float32)
-    return _fma32(d[..., 2], d[..., 2], _fma32(d[..., 1], d[..., 1], t))
+    t = (d[..., 1] * d[..., 1]).astype(np.float32)
+    return _fma32(d[..., 2], d[..., 2], _fma32(d[..., 0], d[..., 0], t))
 
 
 def dist_cuda2(points, k_candidates=12):
