@@ -392,6 +392,16 @@ def main():
             next_rows["parameter_plumbing"] = bench_params.measure(dev, P, M)
         except Exception as ex:
             next_rows["parameter_plumbing"] = {"error": repr(ex)}
+        try:  # §8(f) rank 4 on an SfM-like cloud
+            import bench_knn
+            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3)
+        except Exception as ex:
+            next_rows["dist_cuda2"] = {"error": repr(ex)}
+        try:  # everything together: the reference's training iteration on the binocular config
+            import bench_iteration
+            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5)
+        except Exception as ex:
+            next_rows["train_iteration"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {
