@@ -121,6 +121,8 @@ class Backend:
         # "rotations") the backward writes its parameter gradients INTO instead of
         # allocating them — how dp.GradientBucket receives gradients without a pack copy.
         self.grad_sink = None
+        # our C-ABI treats NULL dL/ddepth, dL/dalpha as zeros; the reference veneer does not
+        self.accepts_null_grads = prefix == "b3gs_"
         # One persistent C callback; `user` is the slot index (0 geom, 1 binning, 2 image).
         self._tls = threading.local()
         self._cb = _RESIZE_FN(self._resize)
@@ -222,6 +224,9 @@ class Backend:
     ):
         P = int(means3D.size(0))
         H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+        if not self.accepts_null_grads:
+            dL_dout_depth = torch.zeros_like(alphas) if dL_dout_depth is None else dL_dout_depth
+            dL_dout_alpha = torch.zeros_like(alphas) if dL_dout_alpha is None else dL_dout_alpha
         dev = means3D.device
         M = int(sh.size(1)) if sh.dim() >= 2 and sh.size(0) != 0 else 0
         # The reference zero-fills all ten (rasterize_points.cu:158-167); our library

@@ -25,7 +25,7 @@ def _fns():
     global _lib
     if _lib is None:
         lib = _backend.native().lib
-        for name, args in (("b3gs_binocular_forward", [_I, _I, _V, _V, _V, _F, _V, _V]),
+        for name, args in (("b3gs_binocular_forward", [_I, _I, _V, _V, _V, _F, _V, _F, _F, _V, _V]),
                            ("b3gs_binocular_backward", [_I, _I, _V, _V, _V, _F, _V, _F, _F, _V, _V, _V]),
                            ("b3gs_warp_forward", [_I, _I, _I, _V, _V, _V, _V]),
                            ("b3gs_warp_backward", [_I, _I, _I, _V, _V, _V, _V, _V, _V]),
@@ -155,13 +155,14 @@ class _Binocular(torch.autograd.Function):
         H, W = depth.shape[-2:]
         dev = depth.device
         with torch.cuda.device(dev):
-            sums = torch.empty(3, dtype=torch.float64, device=dev)
+            sums = torch.empty(4, dtype=torch.float64, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            k_l1, k_sm = 1.0 / float(3 * H * W), smooth_weight / float((H - 2) * (W - 2))
             _call(_fns().b3gs_binocular_forward, H, W, shifted.data_ptr(), depth.data_ptr(), gt.data_ptr(), k_disp,
-                  sums.data_ptr(), _stream(dev))
+                  sums.data_ptr(), k_l1, k_sm, loss.data_ptr(), _stream(dev))
         ctx.save_for_backward(shifted, depth, gt)
-        k_l1, k_sm = 1.0 / float(3 * H * W), smooth_weight / float((H - 2) * (W - 2))
         ctx.meta = (H, W, k_disp, k_l1, k_sm)
-        return (k_l1 * sums[0] + k_sm * (sums[1] + sums[2])).to(torch.float32)
+        return loss
 
     @staticmethod
     def backward(ctx, g):

@@ -315,7 +315,7 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
     if (P == 0) return B3GS_OK;
     if (!geom_buffer || !image_buffer || (!binning_buffer && R > 0))
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null state buffer");
-    if (!dL_dpix || !dL_dpix_depth || !dL_dalphas || !alphas || !radii || !means3D || !background)
+    if (!dL_dpix || !alphas || !radii || !means3D || !background)  // dL_dpix_depth / dL_dalphas: NULL == zeros
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null required input pointer");
     if (!dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_ddepth || !dL_dmean3D || !dL_dcov3D ||
         !dL_dscale || !dL_drot || (M > 0 && shs && !dL_dsh))

@@ -171,7 +171,8 @@ __device__ __forceinline__ float smooth_backward_term(const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads) binocular_forward_kernel(int H, int W, const float* __restrict__ shifted,
                                                                     const float* __restrict__ depth,
                                                                     const float* __restrict__ gt, float k_disp,
-                                                                    double* __restrict__ sums) {
+                                                                    double* __restrict__ sums, float k_l1, float k_sm,
+                                                                    float* __restrict__ loss_out) {
     __shared__ float s_red[kThreads / 32];
     const int tid = threadIdx.y * kBX + threadIdx.x;
     float tx, ty;
@@ -197,6 +198,15 @@ __global__ void __launch_bounds__(kThreads) binocular_forward_kernel(int H, int 
         atomicAdd(sums + 0, (double)b0);
         atomicAdd(sums + 1, (double)b1);
         atomicAdd(sums + 2, (double)b2);
+        if (loss_out) {  // the last block to finish forms the loss value
+            __threadfence();
+            const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(sums + 3), 1ull);
+            if (ticket == (unsigned long long)gridDim.x * gridDim.y - 1) {
+                __threadfence();
+                const volatile double* v = sums;
+                *loss_out = (float)((double)k_l1 * v[0] + (double)k_sm * (v[1] + v[2]));
+            }
+        }
     }
 }
 
@@ -332,11 +342,12 @@ using namespace b3;
 extern "C" {
 
 int b3gs_binocular_forward(int H, int W, const float* shifted, const float* depth, const float* gt, float k_disp,
-                           double* sums, void* stream) {
+                           double* sums, float k_l1, float k_sm, float* loss_out, void* stream) {
     if (H < 3 || W < 3 || !shifted || !depth || !gt || !sums) return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(sums, 0, 3 * sizeof(double), st) != cudaSuccess) return -2;
-    binocular_forward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, shifted, depth, gt, k_disp, sums);
+    if (cudaMemsetAsync(sums, 0, 4 * sizeof(double), st) != cudaSuccess) return -2;
+    binocular_forward_kernel<<<tile_grid(W, H), dim3(kBX, kBY), 0, st>>>(H, W, shifted, depth, gt, k_disp, sums, k_l1,
+                                                                        k_sm, loss_out);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -7,12 +7,12 @@
 // The reference runs five depthwise 11x11 conv2d calls plus ~15 elementwise kernels in
 // the forward and their autograd duals in the backward.  Here:
 //
-//   photometric_forward_kernel   one pass: per 16x16 tile and channel, loads the 26x26
+//   photometric_forward_kernel   one pass: per 32x32 tile and channel, loads the 42x42
 //       halo of both images into shared memory (zero padding == conv2d padding=5),
-//       separable 11-tap Gaussian (horizontal into shared memory, vertical in
-//       registers) of x, y, x^2, y^2, xy; the SSIM map; the three partial derivatives
+//       separable 11-tap Gaussian of x, y, x^2, y^2, xy, both directions register-blocked
+//       (8 outputs per thread from 18 inputs); the SSIM map; the three partial derivatives
 //       dS/dmu1, dS/dsigma1^2, dS/dsigma12 saved for the backward; block-reduced sums of
-//       the SSIM map and of |x - y|.
+//       the SSIM map and of |x - y|; the last block forms the loss value.
 //   photometric_backward_kernel  one pass: separable convolution of the three saved
 //       derivative maps (the window is symmetric, so correlation == convolution) and
 //       dL/dx = gS * [conv(dS/dmu1) + 2x conv(dS/dsigma1^2) + y conv(dS/dsigma12)]
@@ -27,7 +27,15 @@
 
 namespace b3 {
 
-constexpr int kWin = 11, kHalo = 5, kTile = 16, kExt = kTile + 2 * kHalo;  // 26
+// Tile 32x32 outputs per block and channel, halo 5 -> 42x42 inputs.  Both passes of the
+// separable 11-tap filter are register-blocked: a thread produces 8 consecutive outputs
+// along the filter direction from 18 inputs held in registers, so each shared-memory
+// value is loaded once per 8 outputs instead of once per tap (the first revision issued one
+// LDS per FMA and was shared-memory bound at ~7x the HBM time).
+constexpr int kWin = 11, kHalo = 5, kTile = 32, kExt = kTile + 2 * kHalo;  // 42
+constexpr int kSeg = 8, kSegIn = kSeg + kWin - 1;                          // 8 outputs from 18 inputs
+constexpr int kSegs = kTile / kSeg;                                        // 4
+constexpr int kThreads = 256;
 
 // gaussian(11, 1.5) normalised, as float32 exactly as utils/loss_utils.py:26-28 builds it
 __constant__ float kGauss[kWin] = {0.001028380123898387f,  0.0075987582094967365f, 0.036000773310661316f,
@@ -35,104 +43,150 @@ __constant__ float kGauss[kWin] = {0.001028380123898387f,  0.0075987582094967365
                                    0.21300552785396576f,   0.10936068743467331f,   0.036000773310661316f,
                                    0.0075987582094967365f, 0.001028380123898387f};
 
-// tid: linear thread index of the 16x16 block
-__device__ __forceinline__ float block_sum_256(float v, float* s_red, int tid) {
+// out[i] = sum_k w[k] * in[i + k], i < 8
+__device__ __forceinline__ void conv8(const float (&in)[kSegIn], float (&out)[kSeg]) {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    const int lane = tid & 31, warp = tid >> 5;
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    float t = (tid < 8) ? s_red[tid] : 0.f;
-    if (warp == 0) {
+    for (int i = 0; i < kSeg; i++) out[i] = 0.f;
 #pragma unroll
-        for (int d = 4; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    for (int k = 0; k < kWin; k++) {
+        const float w = kGauss[k];
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) out[i] = fmaf(w, in[i + k], out[i]);
     }
-    __syncthreads();
-    return t;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(256) photometric_forward_kernel(int H, int W, const float* __restrict__ img1,
-                                                                 const float* __restrict__ img2,
-                                                                 float* __restrict__ dm_dmu1,
-                                                                 float* __restrict__ dm_dsigma1,
-                                                                 float* __restrict__ dm_dsigma12,
-                                                                 float* __restrict__ ssim_map /* may be null */,
-                                                                 double* __restrict__ sums /* [0] ssim, [1] l1 */) {
-    __shared__ float s1[kExt][kExt + 1], s2[kExt][kExt + 1];
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Adds the block's partial sums and, in the last block to finish, turns the totals into the
+// loss value: loss = k[0] + k[1] * sums[0] + k[2] * sums[1].  sums[2] is the block ticket.
+__device__ __forceinline__ void finish_sums(double* sums, float s0, float s1, unsigned n_blocks, float k0, float k1,
+                                            float k2, float* loss_out) {
+    atomicAdd(sums + 0, (double)s0);
+    atomicAdd(sums + 1, (double)s1);
+    if (!loss_out) return;
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(sums + 2), 1ull);
+    if (ticket == n_blocks - 1) {
+        __threadfence();
+        const double a = *reinterpret_cast<volatile double*>(sums + 0), b = *reinterpret_cast<volatile double*>(sums + 1);
+        *loss_out = (float)((double)k0 + (double)k1 * a + (double)k2 * b);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
+    int H, int W, const float* __restrict__ img1, const float* __restrict__ img2, float* __restrict__ dm_dmu1,
+    float* __restrict__ dm_dsigma1, float* __restrict__ dm_dsigma12, float* __restrict__ ssim_map /* may be null */,
+    double* __restrict__ sums /* [0] ssim, [1] l1, [2] ticket */, float k0, float k1, float k2,
+    float* __restrict__ loss_out /* may be null */) {
+    __shared__ float s1[kExt][kExt + 1], s2[kExt][kExt + 1];  // 43-word rows: conflict-free segment reads
     __shared__ float h[5][kExt][kTile + 1];
-    __shared__ float s_red[8];
+    __shared__ float s_red[2][kThreads / 32];
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
     const size_t plane = (size_t)H * W;
     const float* p1 = img1 + c * plane;
     const float* p2 = img2 + c * plane;
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    for (int i = tid; i < kExt * kExt; i += 256) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kExt * kExt; i += kThreads) {
         const int ly = i / kExt, lx = i - ly * kExt;
         const int gy = y0 + ly - kHalo, gx = x0 + lx - kHalo;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;   // zero padding == conv2d padding=5
         s1[ly][lx] = in ? p1[(size_t)gy * W + gx] : 0.f;
         s2[ly][lx] = in ? p2[(size_t)gy * W + gx] : 0.f;
     }
     __syncthreads();
-    // horizontal pass: 26 rows x 16 columns
-    for (int i = tid; i < kExt * kTile; i += 256) {
-        const int ly = i / kTile, lx = i - ly * kTile;
-        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+    // horizontal pass: 42 rows x 4 segments of 8 outputs
+    if (tid < kExt * kSegs) {
+        const int r = tid / kSegs, sx = (tid - r * kSegs) * kSeg;
+        float a[kSegIn], b[kSegIn], t[kSegIn], o[kSeg];
 #pragma unroll
-        for (int k = 0; k < kWin; k++) {
-            const float w = kGauss[k], u = s1[ly][lx + k], v = s2[ly][lx + k];
-            a = fmaf(w, u, a); b = fmaf(w, v, b);
-            aa = fmaf(w, u * u, aa); bb = fmaf(w, v * v, bb); ab = fmaf(w, u * v, ab);
-        }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = aa; h[3][ly][lx] = bb; h[4][ly][lx] = ab;
+        for (int j = 0; j < kSegIn; j++) { a[j] = s1[r][sx + j]; b[j] = s2[r][sx + j]; }
+        conv8(a, o);
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) h[0][r][sx + i] = o[i];
+        conv8(b, o);
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) h[1][r][sx + i] = o[i];
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) t[j] = a[j] * a[j];
+        conv8(t, o);
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) h[2][r][sx + i] = o[i];
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) t[j] = b[j] * b[j];
+        conv8(t, o);
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) h[3][r][sx + i] = o[i];
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) t[j] = a[j] * b[j];
+        conv8(t, o);
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) h[4][r][sx + i] = o[i];
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int gx = x0 + lx, gy = y0 + ly;
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    // vertical pass: 32 columns x 4 segments of 8 outputs (threads 0..127), then the SSIM map
+    float ssim_sum = 0.f, l1_sum = 0.f;
+    if (tid < kTile * kSegs) {
+        const int lx = tid & (kTile - 1), sy = (tid / kTile) * kSeg;
+        float in[kSegIn], mu1[kSeg], mu2[kSeg], e11[kSeg], e22[kSeg], e12[kSeg];
 #pragma unroll
-    for (int k = 0; k < kWin; k++) {
-        const float w = kGauss[k];
-        mu1 = fmaf(w, h[0][ly + k][lx], mu1);
-        mu2 = fmaf(w, h[1][ly + k][lx], mu2);
-        e11 = fmaf(w, h[2][ly + k][lx], e11);
-        e22 = fmaf(w, h[3][ly + k][lx], e22);
-        e12 = fmaf(w, h[4][ly + k][lx], e12);
+        for (int j = 0; j < kSegIn; j++) in[j] = h[0][sy + j][lx];
+        conv8(in, mu1);
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) in[j] = h[1][sy + j][lx];
+        conv8(in, mu2);
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) in[j] = h[2][sy + j][lx];
+        conv8(in, e11);
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) in[j] = h[3][sy + j][lx];
+        conv8(in, e22);
+#pragma unroll
+        for (int j = 0; j < kSegIn; j++) in[j] = h[4][sy + j][lx];
+        conv8(in, e12);
+        const int gx = x0 + lx;
+#pragma unroll
+        for (int i = 0; i < kSeg; i++) {
+            const int gy = y0 + sy + i;
+            if (gx < W && gy < H) {
+                const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+                const float mu1_sq = mu1[i] * mu1[i], mu2_sq = mu2[i] * mu2[i], mu1_mu2 = mu1[i] * mu2[i];
+                const float sigma1_sq = e11[i] - mu1_sq, sigma2_sq = e22[i] - mu2_sq, sigma12 = e12[i] - mu1_mu2;
+                const float A = 2.f * mu1_mu2 + C1, B = 2.f * sigma12 + C2;
+                const float Cc = mu1_sq + mu2_sq + C1, Dd = sigma1_sq + sigma2_sq + C2;
+                const float inv = 1.f / (Cc * Dd);
+                const float ssim_v = A * B * inv;
+                const size_t o = c * plane + (size_t)gy * W + gx;
+                // dS/dmu1 (through A, B = f(sigma12), Cc, Dd = f(sigma1_sq)); dS/d(E[x^2]); dS/d(E[xy])
+                dm_dmu1[o] = 2.f * mu2[i] * (B - A) * inv - ssim_v * 2.f * mu1[i] * (1.f / Cc - 1.f / Dd);
+                dm_dsigma1[o] = -ssim_v / Dd;
+                dm_dsigma12[o] = 2.f * A * inv;
+                if (ssim_map) ssim_map[o] = ssim_v;
+                ssim_sum += ssim_v;
+                l1_sum += fabsf(s1[sy + i + kHalo][lx + kHalo] - s2[sy + i + kHalo][lx + kHalo]);
+            }
+        }
     }
-    float ssim_v = 0.f, l1_v = 0.f;
-    if (gx < W && gy < H) {
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
-        const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
-        const float A = 2.f * mu1_mu2 + C1, B = 2.f * sigma12 + C2;
-        const float Cc = mu1_sq + mu2_sq + C1, Dd = sigma1_sq + sigma2_sq + C2;
-        const float inv = 1.f / (Cc * Dd);
-        ssim_v = A * B * inv;
-        const size_t o = c * plane + (size_t)gy * W + gx;
-        // dS/dmu1 (through A, B = f(sigma12), Cc, Dd = f(sigma1_sq)); dS/d(E[x^2]); dS/d(E[xy])
-        dm_dmu1[o] = 2.f * mu2 * (B - A) * inv - ssim_v * 2.f * mu1 * (1.f / Cc - 1.f / Dd);
-        dm_dsigma1[o] = -ssim_v / Dd;
-        dm_dsigma12[o] = 2.f * A * inv;
-        if (ssim_map) ssim_map[o] = ssim_v;
-        l1_v = fabsf(s1[ly + kHalo][lx + kHalo] - s2[ly + kHalo][lx + kHalo]);
-    }
-    const float bs = block_sum_256(ssim_v, s_red, tid);
-    const float bl = block_sum_256(l1_v, s_red, tid);
+    ssim_sum = warp_sum(ssim_sum);
+    l1_sum = warp_sum(l1_sum);
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = ssim_sum; s_red[1][tid >> 5] = l1_sum; }
+    __syncthreads();
     if (tid == 0) {
-        atomicAdd(sums + 0, (double)bs);
-        atomicAdd(sums + 1, (double)bl);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTile * kSegs / 32; w++) { a += s_red[0][w]; b += s_red[1][w]; }
+        finish_sums(sums, a, b, gridDim.x * gridDim.y * gridDim.z, k0, k1, k2, loss_out);
     }
 }
 
-__global__ void __launch_bounds__(256) photometric_backward_kernel(int H, int W, const float* __restrict__ img1,
-                                                                  const float* __restrict__ img2,
-                                                                  const float* __restrict__ dm_dmu1,
-                                                                  const float* __restrict__ dm_dsigma1,
-                                                                  const float* __restrict__ dm_dsigma12,
-                                                                  const float* __restrict__ upstream /* device float[1] */, float k_ssim,
-                                                                  float k_l1,
-                                                                  float* __restrict__ dL_dimg1) {
+__global__ void __launch_bounds__(kThreads) photometric_backward_kernel(
+    int H, int W, const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ dm_dmu1,
+    const float* __restrict__ dm_dsigma1, const float* __restrict__ dm_dsigma12,
+    const float* __restrict__ upstream /* device float[1] */, float k_ssim, float k_l1, float* __restrict__ dL_dimg1) {
     __shared__ float s[3][kExt][kExt + 1];
     __shared__ float h[3][kExt][kTile + 1];
     const int c = blockIdx.z;
@@ -141,8 +195,8 @@ __global__ void __launch_bounds__(256) photometric_backward_kernel(int H, int W,
     const float* m0 = dm_dmu1 + c * plane;
     const float* m1 = dm_dsigma1 + c * plane;
     const float* m2 = dm_dsigma12 + c * plane;
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    for (int i = tid; i < kExt * kExt; i += 256) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kExt * kExt; i += kThreads) {
         const int ly = i / kExt, lx = i - ly * kExt;
         const int gy = y0 + ly - kHalo, gx = x0 + lx - kHalo;
         const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -152,36 +206,44 @@ __global__ void __launch_bounds__(256) photometric_backward_kernel(int H, int W,
         s[2][ly][lx] = in ? m2[o] : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < kExt * kTile; i += 256) {
-        const int ly = i / kTile, lx = i - ly * kTile;
-        float a = 0.f, b = 0.f, d = 0.f;
+    if (tid < kExt * kSegs) {
+        const int r = tid / kSegs, sx = (tid - r * kSegs) * kSeg;
+        float in[kSegIn], o[kSeg];
 #pragma unroll
-        for (int k = 0; k < kWin; k++) {
-            const float w = kGauss[k];
-            a = fmaf(w, s[0][ly][lx + k], a);
-            b = fmaf(w, s[1][ly][lx + k], b);
-            d = fmaf(w, s[2][ly][lx + k], d);
+        for (int q = 0; q < 3; q++) {
+#pragma unroll
+            for (int j = 0; j < kSegIn; j++) in[j] = s[q][r][sx + j];
+            conv8(in, o);
+#pragma unroll
+            for (int i = 0; i < kSeg; i++) h[q][r][sx + i] = o[i];
         }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = d;
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int gx = x0 + lx, gy = y0 + ly;
-    if (gx >= W || gy >= H) return;
-    float a = 0.f, b = 0.f, d = 0.f;
+    if (tid >= kTile * kSegs) return;
+    const int lx = tid & (kTile - 1), sy = (tid / kTile) * kSeg;
+    float in[kSegIn], a[kSeg], b[kSeg], d[kSeg];
 #pragma unroll
-    for (int k = 0; k < kWin; k++) {
-        const float w = kGauss[k];
-        a = fmaf(w, h[0][ly + k][lx], a);
-        b = fmaf(w, h[1][ly + k][lx], b);
-        d = fmaf(w, h[2][ly + k][lx], d);
-    }
-    const size_t o = c * plane + (size_t)gy * W + gx;
-    const float x = img1[o], y = img2[o];
+    for (int j = 0; j < kSegIn; j++) in[j] = h[0][sy + j][lx];
+    conv8(in, a);
+#pragma unroll
+    for (int j = 0; j < kSegIn; j++) in[j] = h[1][sy + j][lx];
+    conv8(in, b);
+#pragma unroll
+    for (int j = 0; j < kSegIn; j++) in[j] = h[2][sy + j][lx];
+    conv8(in, d);
+    const int gx = x0 + lx;
+    if (gx >= W) return;
     const float g = upstream[0], gS = g * k_ssim, gL1 = g * k_l1;
-    const float diff = x - y;
-    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
-    dL_dimg1[o] = gS * (a + 2.f * x * b + y * d) + gL1 * sgn;
+#pragma unroll
+    for (int i = 0; i < kSeg; i++) {
+        const int gy = y0 + sy + i;
+        if (gy >= H) break;
+        const size_t o = c * plane + (size_t)gy * W + gx;
+        const float x = img1[o], y = img2[o];
+        const float diff = x - y;
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
+        dL_dimg1[o] = gS * (a[i] + 2.f * x * b[i] + y * d[i]) + gL1 * sgn;
+    }
 }
 
 }  // namespace b3
@@ -191,13 +253,14 @@ using namespace b3;
 extern "C" {
 
 int b3gs_photometric_forward(int C, int H, int W, const float* img1, const float* img2, float* dm_dmu1,
-                             float* dm_dsigma1_sq, float* dm_dsigma12, float* ssim_map, double* sums, void* stream) {
+                             float* dm_dsigma1_sq, float* dm_dsigma12, float* ssim_map, double* sums, float k_const,
+                             float k_ssim, float k_l1, float* loss_out, void* stream) {
     if (C <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !sums) return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(sums, 0, 2 * sizeof(double), st) != cudaSuccess) return -2;
-    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, C), block(kTile, kTile);
+    if (cudaMemsetAsync(sums, 0, 3 * sizeof(double), st) != cudaSuccess) return -2;
+    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, C), block(kThreads);
     photometric_forward_kernel<<<grid, block, 0, st>>>(H, W, img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, ssim_map,
-                                                      sums);
+                                                      sums, k_const, k_ssim, k_l1, loss_out);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -210,7 +273,7 @@ int b3gs_photometric_backward(int C, int H, int W, const float* img1, const floa
         !dL_dimg1)
         return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, C), block(kTile, kTile);
+    dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, C), block(kThreads);
     photometric_backward_kernel<<<grid, block, 0, st>>>(H, W, img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, upstream,
                                                        k_ssim, k_l1,
                                                        dL_dimg1);

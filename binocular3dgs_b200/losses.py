@@ -25,7 +25,7 @@ def _fns():
     global _lib
     if _lib is None:
         lib = _backend.native().lib
-        lib.b3gs_photometric_forward.argtypes = [ctypes.c_int] * 3 + [_V] * 8
+        lib.b3gs_photometric_forward.argtypes = [ctypes.c_int] * 3 + [_V] * 7 + [ctypes.c_float] * 3 + [_V] * 2
         lib.b3gs_photometric_forward.restype = ctypes.c_int
         lib.b3gs_photometric_backward.argtypes = [ctypes.c_int] * 3 + [_V] * 6 + [ctypes.c_float] * 2 + [_V] * 2
         lib.b3gs_photometric_backward.restype = ctypes.c_int
@@ -57,17 +57,19 @@ class _Photometric(torch.autograd.Function):
         dev = a.device
         with torch.cuda.device(dev):
             maps = torch.empty((3, C, H, W), dtype=torch.float32, device=dev)
-            sums = torch.empty(2, dtype=torch.float64, device=dev)
+            sums = torch.empty(3, dtype=torch.float64, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            n = float(C * H * W)
+            # loss = const + w_ssim * mean(SSIM) + w_l1 * mean|x-y|, formed by the kernel's last block
             rc = _fns().b3gs_photometric_forward(C, H, W, a.data_ptr(), b.data_ptr(), maps[0].data_ptr(),
                                                  maps[1].data_ptr(), maps[2].data_ptr(), None, sums.data_ptr(),
+                                                 const, w_ssim / n, w_l1 / n, loss.data_ptr(),
                                                  torch.cuda.current_stream(dev).cuda_stream)
         if rc != 0:
             raise RuntimeError(f"b3gs_photometric_forward failed ({rc})")
-        n = float(C * H * W)
         ctx.save_for_backward(a, b, maps)
         ctx.meta = (C, H, W, w_ssim / n, w_l1 / n, img1.shape)
-        # loss = const + w_ssim * mean(SSIM) + w_l1 * mean|x-y|
-        return (const + (w_ssim / n) * sums[0] + (w_l1 / n) * sums[1]).to(torch.float32)
+        return loss
 
     @staticmethod
     def backward(ctx, grad_out):

@@ -75,6 +75,10 @@ def make_surface(_C) -> SimpleNamespace:
             ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
                                   geomBuffer, binningBuffer, imgBuffer, alpha)
             ctx.mark_non_differentiable(radii)
+            if getattr(_C, "accepts_null_grads", False):
+                # outputs that received no gradient arrive as None instead of materialised
+                # zero images (the C-ABI takes NULL for dL/ddepth and dL/dalpha)
+                ctx.set_materialize_grads(False)
             return color, radii, depth, alpha
 
         @staticmethod
@@ -82,6 +86,10 @@ def make_surface(_C) -> SimpleNamespace:
             s = ctx.raster_settings
             (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
              imgBuffer, alpha) = ctx.saved_tensors
+            if grad_color is None:      # only reachable with set_materialize_grads(False)
+                grad_color = torch.zeros((3, s.image_height, s.image_width), dtype=alpha.dtype, device=alpha.device)
+                if grad_depth is None and grad_alpha is None:
+                    grad_depth = torch.zeros_like(alpha)
             # argument order of the C++ entry point (rasterize_points.h:40-65)
             args = (
                 s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp,

@@ -128,7 +128,8 @@ B3GS_API int b3gs_forward(
  *   dL_dmean3D float[P,3], dL_dcov3D float[P,6], dL_dsh float[P,M,3] (or NULL when
  *   M==0), dL_dscale float[P,3], dL_drot float[P,4].
  * Unlike the reference (rasterize_points.cu:158-167) the outputs need NOT be
- * pre-zeroed: every element is written by this call.
+ * pre-zeroed: every element is written by this call.  dL_dpix_depth and dL_dalphas may
+ * be NULL (that image received no gradient: treated as zeros, and not read).
  */
 B3GS_API int b3gs_backward(
     int P, int D, int M, int R,
@@ -219,8 +220,10 @@ B3GS_API int b3gs_profile_read(double* ms_total, unsigned long long* calls, int 
  *
  * b3gs_photometric_forward writes the three per-pixel partial derivatives of the SSIM
  * map (w.r.t. mu1, E[x^2], E[xy]) needed by the backward, optionally the SSIM map itself
- * (NULL to skip), and sums[0] = sum of the SSIM map, sums[1] = sum |img1 - img2| (device
- * doubles, zeroed by the call).
+ * (NULL to skip), sums[0] = sum of the SSIM map, sums[1] = sum |img1 - img2| (sums: device
+ * double[3], zeroed by the call; [2] is the kernel's block counter) and, if loss_out is
+ * not NULL, *loss_out = k_const + k_ssim * sums[0] + k_l1 * sums[1] (device float, written
+ * by the last block: the loss value never needs a separate kernel).
  * b3gs_photometric_backward writes dL/dimg1 = g * (k_ssim * dSSIMsum/dimg1 +
  * k_l1 * sign(img1 - img2)) with g = upstream[0], a DEVICE float so the upstream gradient
  * never has to visit the host (for the combined loss: k_ssim = -lambda/(CHW),
@@ -228,7 +231,7 @@ B3GS_API int b3gs_profile_read(double* ms_total, unsigned long long* calls, int 
  */
 B3GS_API int b3gs_photometric_forward(int C, int H, int W, const float* img1, const float* img2, float* dm_dmu1,
                                       float* dm_dsigma1_sq, float* dm_dsigma12, float* ssim_map, double* sums,
-                                      void* stream);
+                                      float k_const, float k_ssim, float k_l1, float* loss_out, void* stream);
 B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, const float* img2,
                                        const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
                                        const float* upstream, float k_ssim, float k_l1, float* dL_dimg1,
@@ -244,16 +247,19 @@ B3GS_API int b3gs_photometric_backward(int C, int H, int W, const float* img1, c
  *         (utils/loss_utils.py:18-21, :68-91; w = 0.05).
  * Images are float[3,H,W], depth float[H,W]; H, W >= 3.
  *
- * b3gs_binocular_forward zeroes and fills sums[3] (device doubles): [0] = sum over
+ * b3gs_binocular_forward zeroes and fills sums (device double[4]): [0] = sum over
  * 3*H*W of |warped*mask - gt*mask|, [1] / [2] = sums over (H-2)(W-2) of the x / y
- * smoothness terms; the caller forms loss = sums[0]/(3HW) + w*(sums[1]+sums[2])/((H-2)(W-2)).
+ * smoothness terms, [3] the kernel's block counter; if loss_out is not NULL the last block
+ * writes *loss_out = k_l1 * sums[0] + k_sm * (sums[1] + sums[2]) (device float), i.e. the
+ * loss for k_l1 = 1/(3HW), k_sm = w/((H-2)(W-2)).
  * b3gs_binocular_backward recomputes from the same inputs (nothing is saved) and writes
  * dL/dshifted (zeroed by the call, accumulated with float REDs) and dL/ddepth;
  * upstream is a DEVICE float[1] holding the upstream gradient g (it never visits the
  * host); k_l1 = 1/(3HW) and k_sm = w/((H-2)(W-2)) scale the two terms.  Gradient flows to `shifted` and `depth` only.
  */
 B3GS_API int b3gs_binocular_forward(int H, int W, const float* shifted, const float* depth, const float* gt,
-                                    float k_disp, double* sums, void* stream);
+                                    float k_disp, double* sums, float k_l1, float k_sm, float* loss_out,
+                                    void* stream);
 B3GS_API int b3gs_binocular_backward(int H, int W, const float* shifted, const float* depth, const float* gt,
                                      float k_disp, const float* upstream, float k_l1, float k_sm, float* dL_dshifted,
                                      float* dL_ddepth, void* stream);

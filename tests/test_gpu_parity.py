@@ -360,3 +360,32 @@ def test_reference_render_adapter_end_to_end(nat, dev):
     (img.mean() + 0.1 * depth.mean()).backward()
     assert screenspace.grad.shape == (P, 3) and float(screenspace.grad[:, 2].abs().max()) == 0
     assert float(screenspace.grad[radii > 0][:, :2].abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_unused_outputs_pass_null_gradients_and_match_explicit_zeros():
+    """Only the colour image feeds the loss: depth/alpha gradients travel as NULL through the
+    C-ABI (no materialised zero images) and give the same result as explicit zeros."""
+    from binocular3dgs_b200 import _backend
+    from binocular3dgs_b200.rasterizer import make_surface
+    from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene
+    dev = torch.device("cuda:0")
+    scene, cam = make_scene(3000, seed=12).to(dev), make_camera(120, 90).to(dev)
+    bg = torch.zeros(3, device=dev)
+    gc = make_pixel_grads(120, 90, 13)[0].to(dev)
+    S = make_surface(_backend.native())
+
+    def run(only_color):
+        leaves = [t.detach().clone().requires_grad_(True) for t in scene.tensors()]
+        m3, sc, ro, op, sh = leaves
+        m2 = torch.zeros_like(m3, requires_grad=True)
+        color, radii, depth, alpha = S.GaussianRasterizer(util.settings_for(cam, bg, scene.sh_degree))(
+            means3D=m3, means2D=m2, opacities=op, shs=sh, scales=sc, rotations=ro)
+        if only_color:
+            color.backward(gc)
+        else:
+            torch.autograd.backward([color, depth, alpha], [gc, torch.zeros_like(depth), torch.zeros_like(alpha)])
+        return [t.grad for t in leaves] + [m2.grad]
+
+    for a, b in zip(run(True), run(False)):
+        assert util.rel_err(a, b) <= 2e-5

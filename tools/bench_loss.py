@@ -54,7 +54,8 @@ def measure(dev, C=3, H=800, W=800, iters=30, warmup=5):
     # the two kernels alone, through the C-ABI on preallocated buffers
     fns = losses._fns()
     maps = torch.empty((3, C, H, W), device=dev)
-    sums = torch.empty(2, dtype=torch.float64, device=dev)
+    sums = torch.empty(3, dtype=torch.float64, device=dev)
+    loss_out = torch.empty((), device=dev)
     up = torch.ones(1, device=dev)
     grad = torch.empty((C, H, W), device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
@@ -64,7 +65,8 @@ def measure(dev, C=3, H=800, W=800, iters=30, warmup=5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fns.b3gs_photometric_forward(C, H, W, img.data_ptr(), gt.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr(),
-                                     maps[2].data_ptr(), None, sums.data_ptr(), st)
+                                     maps[2].data_ptr(), None, sums.data_ptr(), 0.2, -0.2 / (C * H * W),
+                                     0.8 / (C * H * W), loss_out.data_ptr(), st)
         fns.b3gs_photometric_backward(C, H, W, img.data_ptr(), gt.data_ptr(), maps[0].data_ptr(), maps[1].data_ptr(),
                                       maps[2].data_ptr(), up.data_ptr(), -0.2 / (C * H * W), 0.8 / (C * H * W),
                                       grad.data_ptr(), st)
@@ -168,7 +170,8 @@ def measure_binocular(dev, H=756, W=1008, iters=30, warmup=5, focal_x=815.0, tra
         return sorted(ts)[len(ts) // 2], float(v.detach()), a.grad, d.grad
 
     fns = binocular._fns()
-    sums = torch.empty(3, dtype=torch.float64, device=dev)
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    loss_out = torch.empty((), device=dev)
     up = torch.ones(1, device=dev)
     g_s, g_d = torch.empty_like(shifted), torch.empty_like(depth)
     st = torch.cuda.current_stream(dev).cuda_stream
@@ -178,7 +181,8 @@ def measure_binocular(dev, H=756, W=1008, iters=30, warmup=5, focal_x=815.0, tra
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fns.b3gs_binocular_forward(H, W, shifted.data_ptr(), depth.data_ptr(), gt.data_ptr(), k_disp, sums.data_ptr(), st)
+        fns.b3gs_binocular_forward(H, W, shifted.data_ptr(), depth.data_ptr(), gt.data_ptr(), k_disp, sums.data_ptr(),
+                                   1.0 / (3 * H * W), 0.05 / ((H - 2) * (W - 2)), loss_out.data_ptr(), st)
         fns.b3gs_binocular_backward(H, W, shifted.data_ptr(), depth.data_ptr(), gt.data_ptr(), k_disp,
                                     up.data_ptr(), 1.0 / (3 * H * W), 0.05 / ((H - 2) * (W - 2)), g_s.data_ptr(),
                                     g_d.data_ptr(), st)
