@@ -55,6 +55,39 @@ __device__ __forceinline__ void conv8(const float (&in)[kSegIn], float (&out)[kS
     }
 }
 
+// Stage the 42x42 halo of one image plane into shared memory (zero padding == conv2d
+// padding=5).  When rows are 16-byte aligned (W % 4 == 0 and an aligned base) the halo is
+// read as 42 rows x 12 float4 covering columns [x0-8, x0+40): 2 vector loads per thread
+// instead of 7 scalar ones with their index arithmetic.  Column c of the tile's halo sits at
+// s[row][c + kPadL] in both cases.
+constexpr int kPadL = 3;                         // x0-8 .. x0-6 are loaded but unused
+constexpr int kRowW = kExt + kPadL + 3 + 1;      // 42 + 3 left + 3 right (48 loaded) + 1 pad = 49
+
+__device__ __forceinline__ void stage_plane(float (*s)[kRowW], const float* __restrict__ p, int x0, int y0, int H, int W,
+                                            bool vec, int tid) {
+    if (vec) {
+        for (int i = tid; i < kExt * 12; i += kThreads) {
+            const int ly = i / 12, q = i - ly * 12;
+            const int gy = y0 + ly - kHalo, gx = x0 - 8 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const float4*>(p + (size_t)gy * W + gx);
+            float* d = &s[ly][4 * q];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int i = tid; i < kExt * kExt; i += kThreads) {
+            const int ly = i / kExt, lx = i - ly * kExt;
+            const int gy = y0 + ly - kHalo, gx = x0 + lx - kHalo;
+            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            s[ly][lx + kPadL] = in ? p[(size_t)gy * W + gx] : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ bool rows_aligned(const float* p, int W, size_t plane) {
+    return ((W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -82,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
     float* __restrict__ dm_dsigma1, float* __restrict__ dm_dsigma12, float* __restrict__ ssim_map /* may be null */,
     double* __restrict__ sums /* [0] ssim, [1] l1, [2] ticket */, float k0, float k1, float k2,
     float* __restrict__ loss_out /* may be null */) {
-    __shared__ float s1[kExt][kExt + 1], s2[kExt][kExt + 1];  // 43-word rows: conflict-free segment reads
+    __shared__ float s1[kExt][kRowW], s2[kExt][kRowW];  // 49-word rows: conflict-free segment reads
     __shared__ float h[5][kExt][kTile + 1];
     __shared__ float s_red[2][kThreads / 32];
     const int c = blockIdx.z;
@@ -91,20 +124,16 @@ __global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
     const float* p1 = img1 + c * plane;
     const float* p2 = img2 + c * plane;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kExt * kExt; i += kThreads) {
-        const int ly = i / kExt, lx = i - ly * kExt;
-        const int gy = y0 + ly - kHalo, gx = x0 + lx - kHalo;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;   // zero padding == conv2d padding=5
-        s1[ly][lx] = in ? p1[(size_t)gy * W + gx] : 0.f;
-        s2[ly][lx] = in ? p2[(size_t)gy * W + gx] : 0.f;
-    }
+    const bool vec = rows_aligned(img1, W, plane) && rows_aligned(img2, W, plane);
+    stage_plane(s1, p1, x0, y0, H, W, vec, tid);
+    stage_plane(s2, p2, x0, y0, H, W, vec, tid);
     __syncthreads();
     // horizontal pass: 42 rows x 4 segments of 8 outputs
     if (tid < kExt * kSegs) {
         const int r = tid / kSegs, sx = (tid - r * kSegs) * kSeg;
         float a[kSegIn], b[kSegIn], t[kSegIn], o[kSeg];
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) { a[j] = s1[r][sx + j]; b[j] = s2[r][sx + j]; }
+        for (int j = 0; j < kSegIn; j++) { a[j] = s1[r][sx + j + kPadL]; b[j] = s2[r][sx + j + kPadL]; }
         conv8(a, o);
 #pragma unroll
         for (int i = 0; i < kSeg; i++) h[0][r][sx + i] = o[i];
@@ -167,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
                 dm_dsigma12[o] = 2.f * A * inv;
                 if (ssim_map) ssim_map[o] = ssim_v;
                 ssim_sum += ssim_v;
-                l1_sum += fabsf(s1[sy + i + kHalo][lx + kHalo] - s2[sy + i + kHalo][lx + kHalo]);
+                l1_sum += fabsf(s1[sy + i + kHalo][lx + kHalo + kPadL] - s2[sy + i + kHalo][lx + kHalo + kPadL]);
             }
         }
     }
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) photometric_backward_kernel(
     int H, int W, const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ dm_dmu1,
     const float* __restrict__ dm_dsigma1, const float* __restrict__ dm_dsigma12,
     const float* __restrict__ upstream /* device float[1] */, float k_ssim, float k_l1, float* __restrict__ dL_dimg1) {
-    __shared__ float s[3][kExt][kExt + 1];
+    __shared__ float s[3][kExt][kRowW];
     __shared__ float h[3][kExt][kTile + 1];
     const int c = blockIdx.z;
     const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
@@ -196,15 +225,11 @@ __global__ void __launch_bounds__(kThreads) photometric_backward_kernel(
     const float* m1 = dm_dsigma1 + c * plane;
     const float* m2 = dm_dsigma12 + c * plane;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kExt * kExt; i += kThreads) {
-        const int ly = i / kExt, lx = i - ly * kExt;
-        const int gy = y0 + ly - kHalo, gx = x0 + lx - kHalo;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        const size_t o = (size_t)gy * W + gx;
-        s[0][ly][lx] = in ? m0[o] : 0.f;
-        s[1][ly][lx] = in ? m1[o] : 0.f;
-        s[2][ly][lx] = in ? m2[o] : 0.f;
-    }
+    const bool vec = rows_aligned(dm_dmu1, W, plane) && rows_aligned(dm_dsigma1, W, plane) &&
+                     rows_aligned(dm_dsigma12, W, plane);
+    stage_plane(s[0], m0, x0, y0, H, W, vec, tid);
+    stage_plane(s[1], m1, x0, y0, H, W, vec, tid);
+    stage_plane(s[2], m2, x0, y0, H, W, vec, tid);
     __syncthreads();
     if (tid < kExt * kSegs) {
         const int r = tid / kSegs, sx = (tid - r * kSegs) * kSeg;
@@ -212,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) photometric_backward_kernel(
 #pragma unroll
         for (int q = 0; q < 3; q++) {
 #pragma unroll
-            for (int j = 0; j < kSegIn; j++) in[j] = s[q][r][sx + j];
+            for (int j = 0; j < kSegIn; j++) in[j] = s[q][r][sx + j + kPadL];
             conv8(in, o);
 #pragma unroll
             for (int i = 0; i < kSeg; i++) h[q][r][sx + i] = o[i];

@@ -71,3 +71,18 @@ opt = parameters.FusedAdam([{"params": [v], "lr": 1e-3} for v in raw.values()], 
 print("FusedAdam.step us/call:", round(wall(opt.step), 1))
 opt2 = torch.optim.Adam([{"params": [v], "lr": 1e-3} for v in raw.values()], lr=0.0, eps=1e-15)
 print("torch Adam.step us/call:", round(wall(opt2.step), 1))
+
+if os.environ.get("B3GS_CPROFILE"):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    for _ in range(50):
+        step_l1()
+    torch.cuda.synchronize()
+    pr.enable()
+    for _ in range(300):
+        step_l1()
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr)
+    st.sort_stats("cumulative").print_stats(45)
