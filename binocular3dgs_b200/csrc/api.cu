@@ -340,6 +340,7 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
     if (R > 0) {
         CompositeBwdArgs ca;
         ca.W = width; ca.H = height; ca.grid_x = grid_x; ca.grid_y = grid_y;
+        ca.P = P; ca.R = R;
         ca.ranges = reinterpret_cast<const uint2*>(img + il.ranges);
         ca.point_list = reinterpret_cast<const uint32_t*>(bin + bl.point_list);
         ca.records = reinterpret_cast<const float4*>(geo + gl.records);

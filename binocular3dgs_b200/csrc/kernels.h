@@ -89,6 +89,7 @@ void launch_composite_forward(const CompositeFwdArgs& a, cudaStream_t stream);
 
 struct CompositeBwdArgs {
     int W, H, grid_x, grid_y;
+    int P, R;                       // Gaussians and tile instances (kernel-shape heuristic only)
     const uint2* ranges;
     const uint32_t* point_list;
     const float4* records;          // a/b from the forward; colours may be overridden
