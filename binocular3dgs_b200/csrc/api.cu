@@ -442,6 +442,8 @@ int b3gs_profile_read(double* ms_total, unsigned long long* calls, int n) {
     return (int)pend.size();
 }
 
+void b3gs_set_backward_pixels(int n) { b3::set_backward_pixels(n); }
+
 const char* b3gs_last_error(void) { return g_error.c_str(); }
 const char* b3gs_version(void) { return "b3gs 0.1 (sm_100a)"; }
 unsigned long long b3gs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -103,6 +103,7 @@ struct CompositeBwdArgs {
     float* grads;                   // [P, B3_GRAD_STRIDE], zeroed by the caller
 };
 void launch_composite_backward(const CompositeBwdArgs& a, cudaStream_t stream);
+void set_backward_pixels(int n);  // 0 = automatic
 
 // ---------------------------------------------------------------- K8 + K9 fused
 struct PreBackwardArgs {

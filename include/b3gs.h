@@ -342,6 +342,12 @@ B3GS_API size_t b3gs_dist_cuda2_scratch_bytes(int P);
 B3GS_API int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,
                              void* stream);
 
+/* The composite backward exists in three shapes — 1, 2 or 4 pixels per lane (8x4, 8x8, 16x8
+ * pixels per warp) — with identical results up to float summation order; n = 0 (default)
+ * picks per call from the instances-per-Gaussian ratio, n = 1|2|4 forces one (tests, A/B
+ * timing; also the environment variable B3GS_BWD_PIX at load time). */
+B3GS_API void b3gs_set_backward_pixels(int n);
+
 /* Last error message of the calling thread ("" if none). */
 B3GS_API const char* b3gs_last_error(void);
 

@@ -389,3 +389,26 @@ def test_unused_outputs_pass_null_gradients_and_match_explicit_zeros():
 
     for a, b in zip(run(True), run(False)):
         assert util.rel_err(a, b) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_backward_kernel_shapes_agree():
+    """The backward exists with 1, 2 and 4 pixels per lane (chosen per call from the
+    instances-per-Gaussian ratio); all three must give the same gradients up to float
+    summation order, on a ragged image (tile rows/columns cut by the border)."""
+    from binocular3dgs_b200 import _backend
+    nat = _backend.native()
+    dev = torch.device("cuda:0")
+    scene, cam = make_scene(20000, seed=21).to(dev), make_camera(333, 190).to(dev)
+    bg = torch.tensor([0.2, 0.1, 0.3], device=dev)
+    grads = tuple(g.to(dev) for g in make_pixel_grads(333, 190, 22))
+    outs = {}
+    try:
+        for n in (1, 2, 4):
+            nat.lib.b3gs_set_backward_pixels(n)
+            outs[n] = util.surface_forward_backward(nat, scene, cam, bg, grads)
+    finally:
+        nat.lib.b3gs_set_backward_pixels(0)
+    for n in (2, 4):
+        for k in GRAD_KEYS:
+            assert util.rel_err(outs[n][k], outs[1][k]) <= 5e-5, (n, k)
