@@ -185,3 +185,26 @@ def test_fused_loss_full_size_vs_oracle():
         err = np.abs(got - want) / np.abs(want).max()
         assert (err > 3e-4).mean() < 5e-5, float((err > 3e-4).mean())
         assert np.median(err) < 1e-6
+
+
+@pytest.mark.gpu
+def test_warp_batch_and_noncontiguous_inputs():
+    """inverse_warp_images loops over the batch like the reference (graphics_utils.py:91);
+    non-contiguous inputs are accepted (made contiguous on the host side)."""
+    from binocular3dgs_b200 import binocular
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(2, 3, 19, 40, generator=g)
+    disp = (torch.rand(2, 1, 19, 40, generator=g) - 0.5) * 30.0
+    got = binocular.inverse_warp_images(img.cuda(), disp.cuda()).cpu().numpy()
+    for b in range(2):
+        assert np.abs(got[b] - bo.inverse_warp(img[b].numpy(), disp[b, 0].numpy())).max() < WARP_TOL
+    wide = torch.rand(1, 3, 19, 80, generator=g).cuda()
+    a = binocular.inverse_warp_images(wide[..., ::2], disp[:1].cuda())
+    b = binocular.inverse_warp_images(wide[..., ::2].contiguous(), disp[:1].cuda())
+    assert torch.equal(a, b)
+    # an all-invalid disparity map warps to zeros and passes no gradient
+    x = torch.rand(1, 3, 8, 16).cuda().requires_grad_(True)
+    d = torch.full((1, 1, 8, 16), 1000.0).cuda().requires_grad_(True)
+    y = binocular.inverse_warp_images(x, d)
+    y.sum().backward()
+    assert float(y.abs().max()) == 0.0 and float(x.grad.abs().max()) == 0.0 and float(d.grad.abs().max()) == 0.0

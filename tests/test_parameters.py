@@ -216,3 +216,27 @@ def test_activate_full_size_vs_oracle_and_partial_gradients():
     assert rel(params["rotation"].grad.cpu().numpy(), gw[4]) < TOL
     for k in ("opacity", "scaling"):
         assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_fused_adam_skips_parameters_without_gradient_and_handles_odd_sizes():
+    """A group whose parameter has no .grad keeps its state untouched (torch semantics);
+    sizes that are not multiples of 4 and unaligned views take the scalar path."""
+    from binocular3dgs_b200 import parameters
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1001 * 3 + 1, generator=g).cuda()
+    pa = [torch.nn.Parameter(base[1:].clone().view(1001, 3)), torch.nn.Parameter(torch.randn(7, generator=g).cuda()),
+          torch.nn.Parameter(torch.randn(5, 4, generator=g).cuda())]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam([{"params": [p], "lr": 0.01 * (i + 1)} for i, p in enumerate(pa)], lr=0.0, eps=1e-15)
+    ob = parameters.FusedAdam([{"params": [p], "lr": 0.01 * (i + 1)} for i, p in enumerate(pb)], lr=0.0, eps=1e-15)
+    for step in range(3):
+        for plist in (pa, pb):
+            gen = torch.Generator().manual_seed(50 + step)
+            for i, p in enumerate(plist):
+                p.grad = None if (i == 1 and step != 1) else torch.randn(p.shape, generator=gen).cuda()
+        oa.step()
+        ob.step()
+    for a, b in zip(pa, pb):
+        assert float((a - b).abs().max()) < 1e-6
+    assert float(oa.state[pa[1]]["step"]) == float(ob.state[pb[1]]["step"]) == 1.0
