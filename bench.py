@@ -153,7 +153,10 @@ def main():
     else:
         from binocular3dgs_b200 import _backend
         back = _backend.native()
-    S = make_surface(back)
+    # the public surface (e2e) runs on the compiled host side when it has been built; the
+    # device-timed loop below drives the C-ABI through the ctypes host side (per-stage
+    # profiling, the DP gradient sink) — same library, same kernels
+    S = make_surface(_backend.preferred() if args.impl == "native" else back)
 
     cfg = CONFIGS[args.config]
     W, H, P = cfg["width"], cfg["height"], cfg["P"]

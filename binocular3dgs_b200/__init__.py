@@ -9,7 +9,7 @@ PyTorch fallback, a missing library is an ImportError.
 from . import _backend
 from .rasterizer import GaussianRasterizationSettings, cpu_deep_copy_tuple, make_surface
 
-_C = _backend.native()
+_C = _backend.preferred()
 _surface = make_surface(_C)
 _RasterizeGaussians = _surface._RasterizeGaussians
 rasterize_gaussians = _surface.rasterize_gaussians

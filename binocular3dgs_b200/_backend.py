@@ -299,6 +299,55 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb3gs.so")
 
 _native = None
+_compiled = None
+COMPILED_PATH = os.path.join(_HERE, "_b3gs_torch.so")
+
+
+class CompiledBackend:
+    """The same ``_C`` surface served by the compiled host side (csrc/torch_binding.cpp, a
+    pybind11 module over the identical C-ABI calls): ~4x less host time per call than the
+    ctypes path, which matters because the host is on the critical path after the forward's
+    synchronisation.  Everything that is not one of the three operator entry points
+    (profiling, blob slicing for the parity tests, the DP gradient sink) is delegated to the
+    ctypes ``Backend`` bound to the same ``libb3gs.so``."""
+
+    accepts_null_grads = True
+
+    def __init__(self, module, ctypes_backend: Backend):
+        self._m = module
+        self._ct = ctypes_backend
+        self.name, self.prefix, self.path = "b3gs(compiled host)", ctypes_backend.prefix, COMPILED_PATH
+        self.needs_zeroed_outputs = False
+        self.rasterize_gaussians = module.rasterize_gaussians
+        self.mark_visible = module.mark_visible
+
+    def rasterize_gaussians_backward(self, *args):
+        if self._ct.grad_sink is not None:      # gradients go straight into the DP bucket
+            return self._ct.rasterize_gaussians_backward(*args)
+        return self._m.rasterize_gaussians_backward(*args)
+
+    def __getattr__(self, name):                # lib, launch_count, profile_*, blob_view, grad_sink, ...
+        return getattr(self._ct, name)
+
+
+def preferred():
+    """The compiled host side if it has been built (``__graft_entry__.build()``), else the
+    ctypes one.  Both call the same kernels in the same ``libb3gs.so``."""
+    global _compiled
+    if _compiled is None:
+        ct = native()
+        _compiled = ct
+        if os.path.exists(COMPILED_PATH) and os.environ.get("B3GS_HOST", "compiled") != "ctypes":
+            import importlib.util
+            try:
+                spec = importlib.util.spec_from_file_location("_b3gs_torch", COMPILED_PATH)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _compiled = CompiledBackend(mod, ct)
+            except (ImportError, OSError) as ex:      # stale build against another torch: keep ctypes, say so
+                import warnings
+                warnings.warn(f"binocular3dgs_b200: compiled host side not loadable ({ex}); using the ctypes one")
+    return _compiled
 
 
 def native() -> Backend:

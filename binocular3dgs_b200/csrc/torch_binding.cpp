@@ -1,0 +1,152 @@
+// torch_binding.cpp — the compiled host side above the C-ABI: a pybind11 module with the
+// reference's `_C` functions, same names, argument order and return tuples
+// (submodules/diff-gaussian-rasterization/ext.cpp:15-18, rasterize_points.h:18-70).
+//
+// It does what rasterize_points.cu:35-229 does — allocate the outputs and the three opaque
+// blobs as torch tensors (the blobs through resize callbacks, rasterize_points.cu:27-33),
+// unwrap data pointers, call the library — but the library it calls is libb3gs.so through
+// include/b3gs.h, on torch's CURRENT stream.  There is no kernel code in this file.
+//
+// binocular3dgs_b200/_backend.py implements the same surface with ctypes and stays the
+// reference implementation of the host side (and the only one the parity tests use to drive
+// the reference's kernels); this module exists because the host side is on the critical
+// path: after the forward's one host synchronisation the GPU has ~250 us of work queued, and
+// everything the host does before it enqueues the backward in excess of that is GPU idle
+// time (tools/host_overhead.py).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <stdexcept>
+#include <string>
+#include <tuple>
+
+#include "../../include/b3gs.h"
+
+namespace {
+
+void* resize_cb(void* user, size_t n) {  // resizeFunctional, rasterize_points.cu:27-33
+    auto* t = static_cast<torch::Tensor*>(user);
+    t->resize_({(long long)n});
+    return t->data_ptr();
+}
+
+// reference null convention (rasterize_points.cu:96-115): empty tensor -> nullptr
+const float* fptr(const torch::Tensor& t, const char* name, torch::Tensor& keep) {
+    if (!t.defined() || t.numel() == 0) return nullptr;
+    TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+    TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+    keep = t.contiguous();
+    return keep.data_ptr<float>();
+}
+
+[[noreturn]] void fail(const char* what, int rc) {
+    throw std::runtime_error(std::string("b3gs.") + what + " failed (" + std::to_string(rc) + "): " + b3gs_last_error());
+}
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rasterize_gaussians(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                    const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
+                    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                    const bool prefiltered, const bool debug) {
+    if (means3D.ndimension() != 2 || means3D.size(1) != 3) AT_ERROR("means3D must have dimensions (num_points, 3)");
+    TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (no CPU path exists)");
+    const int P = (int)means3D.size(0), H = image_height, W = image_width;
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    auto fopt = means3D.options().dtype(torch::kFloat32);
+    auto bopt = means3D.options().dtype(torch::kByte);
+    torch::Tensor out_color = torch::empty({3, H, W}, fopt), out_depth = torch::empty({1, H, W}, fopt),
+                  out_alpha = torch::empty({1, H, W}, fopt),
+                  radii = torch::empty({P}, means3D.options().dtype(torch::kInt32));
+    torch::Tensor geom = torch::empty({0}, bopt), binning = torch::empty({0}, bopt), img = torch::empty({0}, bopt);
+    const int M = (sh.dim() >= 2 && sh.size(0) != 0) ? (int)sh.size(1) : 0;
+    torch::Tensor k[11];
+    int rendered = 0;
+    const int rc = b3gs_forward(
+        b3gs_buffer{resize_cb, &geom}, b3gs_buffer{resize_cb, &binning}, b3gs_buffer{resize_cb, &img}, P, degree, M,
+        fptr(background, "background", k[0]), W, H, fptr(means3D, "means3D", k[1]), fptr(sh, "sh", k[2]),
+        fptr(colors, "colors_precomp", k[3]), fptr(opacity, "opacities", k[4]), fptr(scales, "scales", k[5]),
+        scale_modifier, fptr(rotations, "rotations", k[6]), fptr(cov3D_precomp, "cov3D_precomp", k[7]),
+        fptr(viewmatrix, "viewmatrix", k[8]), fptr(projmatrix, "projmatrix", k[9]), fptr(campos, "campos", k[10]),
+        tan_fovx, tan_fovy, prefiltered ? 1 : 0, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
+        out_alpha.data_ptr<float>(), P ? radii.data_ptr<int>() : nullptr, debug ? 1 : 0,
+        at::cuda::getCurrentCUDAStream().stream(), &rendered);
+    if (rc != 0) fail("rasterize_gaussians", rc);
+    return std::make_tuple(rendered, out_color, out_depth, out_alpha, radii, geom, binning, img);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor>
+rasterize_gaussians_backward(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                             const torch::Tensor& colors, const torch::Tensor& scales, const torch::Tensor& rotations,
+                             const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                             const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                             const float tan_fovy, const torch::Tensor& dL_dout_color,
+                             const c10::optional<torch::Tensor>& dL_dout_depth,
+                             const c10::optional<torch::Tensor>& dL_dout_alpha, const torch::Tensor& sh,
+                             const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                             const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+                             const torch::Tensor& alphas, const bool debug) {
+    const int P = (int)means3D.size(0);
+    const int H = (int)dL_dout_color.size(1), W = (int)dL_dout_color.size(2);
+    const int M = (sh.dim() >= 2 && sh.size(0) != 0) ? (int)sh.size(1) : 0;
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    auto fopt = means3D.options().dtype(torch::kFloat32);
+    // the reference zero-fills all ten (rasterize_points.cu:158-167); the library writes every element
+    auto alloc = [&](at::IntArrayRef s) { return P == 0 ? torch::zeros(s, fopt) : torch::empty(s, fopt); };
+    torch::Tensor dL_dmeans3D = alloc({P, 3}), dL_dmeans2D = alloc({P, 3}), dL_dcolors = alloc({P, 3}),
+                  dL_ddepths = alloc({P, 1}), dL_dconic = alloc({P, 2, 2}), dL_dopacity = alloc({P, 1}),
+                  dL_dcov3D = alloc({P, 6}), dL_dsh = alloc({P, M, 3}), dL_dscales = alloc({P, 3}),
+                  dL_drotations = alloc({P, 4});
+    if (P != 0) {
+        torch::Tensor k[14];
+        torch::Tensor none;
+        torch::Tensor rad = radii.contiguous();
+        const int rc = b3gs_backward(
+            P, degree, M, R, fptr(background, "background", k[0]), W, H, fptr(means3D, "means3D", k[1]),
+            fptr(sh, "sh", k[2]), fptr(colors, "colors_precomp", k[3]), fptr(alphas, "alphas", k[4]),
+            fptr(scales, "scales", k[5]), scale_modifier, fptr(rotations, "rotations", k[6]),
+            fptr(cov3D_precomp, "cov3D_precomp", k[7]), fptr(viewmatrix, "viewmatrix", k[8]),
+            fptr(projmatrix, "projmatrix", k[9]), fptr(campos, "campos", k[10]), tan_fovx, tan_fovy, rad.data_ptr<int>(),
+            reinterpret_cast<char*>(geomBuffer.data_ptr()),
+            binningBuffer.numel() ? reinterpret_cast<char*>(binningBuffer.data_ptr()) : nullptr,
+            reinterpret_cast<char*>(imageBuffer.data_ptr()), fptr(dL_dout_color, "dL_dout_color", k[11]),
+            fptr(dL_dout_depth.has_value() ? *dL_dout_depth : none, "dL_dout_depth", k[12]),
+            fptr(dL_dout_alpha.has_value() ? *dL_dout_alpha : none, "dL_dout_alpha", k[13]),
+            dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(), dL_dopacity.data_ptr<float>(),
+            dL_dcolors.data_ptr<float>(), dL_ddepths.data_ptr<float>(), dL_dmeans3D.data_ptr<float>(),
+            dL_dcov3D.data_ptr<float>(), M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
+            dL_drotations.data_ptr<float>(), debug ? 1 : 0, at::cuda::getCurrentCUDAStream().stream());
+        if (rc != 0) fail("rasterize_gaussians_backward", rc);
+    }
+    return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+                           dL_drotations);
+}
+
+torch::Tensor mark_visible(const torch::Tensor& means3D, const torch::Tensor& viewmatrix,
+                           const torch::Tensor& projmatrix) {
+    const int P = (int)means3D.size(0);
+    torch::Tensor present = torch::zeros({P}, means3D.options().dtype(torch::kBool));
+    if (P != 0) {
+        const c10::cuda::CUDAGuard guard(means3D.device());
+        torch::Tensor k[3];
+        const int rc = b3gs_mark_visible(P, fptr(means3D, "means3D", k[0]), fptr(viewmatrix, "viewmatrix", k[1]),
+                                         fptr(projmatrix, "projmatrix", k[2]),
+                                         reinterpret_cast<unsigned char*>(present.data_ptr<bool>()),
+                                         at::cuda::getCurrentCUDAStream().stream());
+        if (rc != 0) fail("mark_visible", rc);
+    }
+    return present;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("rasterize_gaussians", &rasterize_gaussians);
+    m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward);
+    m.def("mark_visible", &mark_visible);
+    m.def("launch_count", []() { return (unsigned long long)b3gs_launch_count(); });
+    m.def("version", []() { return std::string(b3gs_version()); });
+}

@@ -412,3 +412,35 @@ def test_backward_kernel_shapes_agree():
     for n in (2, 4):
         for k in GRAD_KEYS:
             assert util.rel_err(outs[n][k], outs[1][k]) <= 5e-5, (n, k)
+
+
+@pytest.mark.gpu
+def test_compiled_host_side_matches_ctypes_host_side():
+    """csrc/torch_binding.cpp and _backend.py are two host sides over the same C-ABI calls:
+    identical images, radii and blobs' contents; gradients equal up to the order of the
+    float REDs; NULL depth/alpha gradients accepted by both."""
+    from binocular3dgs_b200 import _backend
+    from binocular3dgs_b200.rasterizer import make_surface
+    comp = _backend.preferred()
+    if not isinstance(comp, _backend.CompiledBackend):
+        pytest.skip("compiled host side not built")
+    nat = _backend.native()
+    dev = torch.device("cuda:0")
+    scene, cam = make_scene(5000, seed=31).to(dev), make_camera(160, 120).to(dev)
+    bg = torch.tensor([0.3, 0.2, 0.1], device=dev)
+    grads = tuple(g.to(dev) for g in make_pixel_grads(160, 120, 32))
+    a, b = util.raw_forward(comp, scene, cam, bg), util.raw_forward(nat, scene, cam, bg)
+    assert a["R"] == b["R"]
+    for k in ("color", "depth", "alpha", "radii"):
+        assert torch.equal(a[k], b[k]), k
+    ga = util.surface_forward_backward(comp, scene, cam, bg, grads)
+    gb = util.surface_forward_backward(nat, scene, cam, bg, grads)
+    for k in GRAD_KEYS:
+        assert util.rel_err(ga[k], gb[k]) <= 2e-5, k
+    before = nat.launch_count()
+    assert comp.mark_visible(scene.means3D, cam.world_view_transform, cam.full_proj_transform).dtype == torch.bool
+    assert nat.launch_count() == before + 1          # one library instance behind both
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        comp.rasterize_gaussians(bg, scene.means3D.view(-1), *([torch.empty(0)] * 4), 1.0, torch.empty(0),
+                                 cam.world_view_transform, cam.full_proj_transform, 0.5, 0.5, 8, 8, torch.empty(0), 0,
+                                 cam.camera_center, False, False)

@@ -19,7 +19,8 @@ scene, cam = make_scene(2000, seed=1).to(dev), make_camera(64, 64).to(dev)
 bg = torch.zeros(3, device=dev)
 grads = tuple(g.to(dev) for g in make_pixel_grads(64, 64))
 nat = _backend.native()
-S = make_surface(nat)
+S = make_surface(_backend.native() if os.environ.get("B3GS_HOST") == "ctypes" else _backend.preferred())
+print("host side:", type(S._C).__name__)
 e = torch.empty(0)
 
 
