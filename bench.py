@@ -306,8 +306,8 @@ def main():
         return None
 
     back.grad_sink = None                          # autograd owns the gradient tensors on this path
-    e2e_steps = max(10, args.steps // 2)
-    e2e_warm = max(3, args.warmup // 2)
+    e2e_steps = max(10, args.steps)
+    e2e_warm = max(3, args.warmup)
     for i in range(e2e_warm):
         e2e_step(i)
         flush.zero_()
