@@ -68,7 +68,10 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name} must be float32, got {t.dtype}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:       # a contiguous view at an odd offset: the kernels load float4s
+        t = t.clone()
+    return t
 
 
 class Backend:
@@ -248,7 +251,8 @@ class Backend:
             if sink is not None and P != 0:
                 def take(name, t):
                     v = sink.get(name)
-                    if v is None or v.numel() != t.numel() or v.device != t.device or not v.is_contiguous():
+                    if (v is None or v.numel() != t.numel() or v.device != t.device or not v.is_contiguous()
+                            or v.data_ptr() % 16 != 0):
                         return t
                     if self.needs_zeroed_outputs:
                         v.zero_()

@@ -37,6 +37,7 @@ const float* fptr(const torch::Tensor& t, const char* name, torch::Tensor& keep)
     TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
     TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
     keep = t.contiguous();
+    if (reinterpret_cast<uintptr_t>(keep.data_ptr()) % 16 != 0) keep = keep.clone();  // the kernels load float4s
     return keep.data_ptr<float>();
 }
 

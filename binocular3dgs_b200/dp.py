@@ -28,15 +28,19 @@ class GradientBucket:
         self.P, self.M = int(P), int(M)
         self.widths = {"means3D": 3, "shs": 3 * self.M, "opacities": 1, "scales": 3, "rotations": 4}
         self.floats_per_gaussian = sum(self.widths.values())  # 11 + 3M
-        self.flat = torch.zeros(self.P * self.floats_per_gaussian, dtype=dtype, device=device)
+        # every segment starts on a 16-byte boundary (the backward kernel stores float4s into
+        # the rotation segment); the few padding floats stay zero and ride along in the reduce
+        offsets, off = {}, 0
+        for name in SEGMENTS:
+            offsets[name] = off
+            off += (self.P * self.widths[name] + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=dtype, device=device)
         self._views: Dict[str, torch.Tensor] = {}
-        off = 0
         for name in SEGMENTS:
             n = self.P * self.widths[name]
-            v = self.flat[off:off + n]
+            v = self.flat[offsets[name]:offsets[name] + n]
             shape = (self.P, self.M, 3) if name == "shs" else (self.P, self.widths[name])
             self._views[name] = v.view(shape)
-            off += n
 
     def views(self) -> Dict[str, torch.Tensor]:
         """Tensors aliasing the bucket, one per parameter group."""

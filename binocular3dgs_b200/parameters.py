@@ -68,7 +68,8 @@ def _f32_cuda(t: torch.Tensor, name: str, shape=None) -> torch.Tensor:
         raise RuntimeError(f"{name} must be float32")
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
-    return t.contiguous()
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()      # the kernels load float4s
 
 
 # ------------------------------------------------------------------ activations
@@ -97,7 +98,10 @@ class _Activate(torch.autograd.Function):
         need = ctx.needs_input_grad
 
         def grad_in(g, wanted):
-            return g.contiguous() if (g is not None and wanted) else None
+            if g is None or not wanted:
+                return None
+            g = g.contiguous()
+            return g if g.data_ptr() % 16 == 0 else g.clone()
 
         g_shs = grad_in(g_shs, need[0] or need[1])
         g_opacities, g_scales, g_rotations = grad_in(g_opacities, need[2]), grad_in(g_scales, need[3]), grad_in(g_rotations, need[4])

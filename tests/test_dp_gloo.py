@@ -27,7 +27,9 @@ def _worker(rank, world, port, q):
     from binocular3dgs_b200.dp import SEGMENTS, GradientBucket, reduce_densify_stats, shard_views
     P, M = 257, 4
     bucket = GradientBucket(P, M, device="cpu")
-    assert bucket.floats_per_gaussian == 11 + 3 * M and bucket.nbytes == P * 23 * 4
+    # P = 257 is odd: every segment still starts on a 16-byte boundary (<= 3 padding floats each)
+    assert bucket.floats_per_gaussian == 11 + 3 * M and P * 23 * 4 <= bucket.nbytes <= (P * 23 + 15) * 4
+    assert all((v.data_ptr() - bucket.flat.data_ptr()) % 16 == 0 for v in bucket.views().values())
     views = bucket.views()
     def make_local(r):
         g = torch.Generator().manual_seed(100 + r)
