@@ -46,7 +46,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from binocular3dgs_b200.dp import GradientBucket  # noqa: E402
+from binocular3dgs_b200.dp import GradientBucket, make_bucket  # noqa: E402
 from binocular3dgs_b200.rasterizer import GaussianRasterizationSettings, make_surface  # noqa: E402
 from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
 
@@ -173,7 +173,10 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     e = torch.empty(0)
     use_dp = world > 1 and args.impl == "native"
-    bucket = GradientBucket(P, M, dev) if args.impl == "native" else None
+    # world > 1: the bucket lives in symmetric memory and is reduced by b3gs_peer_allreduce
+    # (B3GS_DP=nccl forces the NCCL all-reduce for A/B timing)
+    bucket, bucket_kind = (make_bucket(P, M, dev, prefer_peer=os.environ.get("B3GS_DP", "peer") != "nccl")
+                           if args.impl == "native" else (None, None))
     if bucket is not None:
         back.grad_sink = bucket.views()
 
@@ -414,8 +417,10 @@ def main():
             "config": {"workload": "%s: %d Gaussians (%s, seed 0, SH degree %d, M=%d), %dx%d, 8 cameras on a ring"
                                    % (args.config, P, args.kind, scene.sh_degree, M, W, H),
                        "P": P, "width": W, "height": H,
-                       "parallelism": ("view-parallel dp%d, NCCL all-reduce of the %d-byte/Gaussian gradient bucket"
-                                       % (world, 4 * (11 + 3 * M))) if use_dp else
+                       "parallelism": ("view-parallel dp%d, %s of the %d-byte/Gaussian gradient bucket"
+                                       % (world, "in-place two-shot all-reduce over NVLink peer memory "
+                                          "(b3gs_peer_allreduce)" if bucket_kind == "peer" else "NCCL all-reduce",
+                                          4 * (11 + 3 * M))) if use_dp else
                                       ("single GPU" if world == 1 else "%d independent replicas" % world),
                        "l2": "flushed between steps (512 MiB memset outside the per-step event pairs)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

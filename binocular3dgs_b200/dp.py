@@ -67,6 +67,76 @@ class GradientBucket:
         return work
 
 
+class PeerGradientBucket(GradientBucket):
+    """The same bucket in SYMMETRIC memory, reduced by this library's own kernel.
+
+    ``flat`` is allocated with ``torch.distributed._symmetric_memory`` so that every rank
+    holds the device pointers of all peers' buckets over NVLink / NVSwitch.  The backward
+    kernel writes into it exactly as into :class:`GradientBucket` (``Backend.grad_sink``);
+    :meth:`all_reduce` is then barrier -> ``b3gs_peer_allreduce`` (one in-place two-shot
+    kernel: each rank reduces its slice from all peers and stores the sum to all peers) ->
+    barrier, all on the current stream.  No NCCL call is on this path.  All ranks of ``group``
+    must construct the bucket collectively.  CUDA only.
+    """
+
+    def __init__(self, P: int, M: int, device, group=None, dtype=torch.float32):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _backend
+        if dtype != torch.float32:
+            raise RuntimeError("PeerGradientBucket is float32 only")
+        super().__init__(P, M, "meta")              # sizes and offsets only
+        group = dist.group.WORLD if group is None else group
+        n = (self.flat.numel() + 3) // 4 * 4
+        self.flat = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self._handle = symm_mem.rendezvous(self.flat, group)
+        self.world, self.rank = self._handle.world_size, self._handle.rank
+        if self.world > 8:
+            raise RuntimeError("b3gs_peer_allreduce supports up to 8 peers (one NVSwitch domain)")
+        self._ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self._handle.buffer_ptrs])
+        self._fn = _backend.native().lib.b3gs_peer_allreduce
+        self._fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t,
+                             ctypes.c_float, ctypes.c_void_p]
+        self._fn.restype = ctypes.c_int
+        off = 0
+        for name in SEGMENTS:
+            cnt = self.P * self.widths[name]
+            shape = (self.P, self.M, 3) if name == "shs" else (self.P, self.widths[name])
+            self._views[name] = self.flat[off:off + cnt].view(shape)
+            off += (cnt + 3) // 4 * 4
+
+    def all_reduce(self, group=None, average: bool = True, async_op: bool = False):
+        if async_op:
+            raise NotImplementedError("the peer all-reduce is stream-ordered; async_op has no meaning here")
+        if self.world == 1:
+            return None
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._handle.barrier(channel=0)        # every peer's backward has written its bucket
+            rc = self._fn(self.world, self.rank, self._ptrs, self.flat.numel(),
+                          (1.0 / self.world) if average else 1.0, stream)
+            if rc != 0:
+                raise RuntimeError(f"b3gs_peer_allreduce failed ({rc})")
+            self._handle.barrier(channel=1)        # every peer's slice has landed everywhere
+        return None
+
+
+def make_bucket(P: int, M: int, device, group=None, prefer_peer: bool = True):
+    """``PeerGradientBucket`` when the process group spans several CUDA ranks and symmetric
+    memory can be set up, else the NCCL/gloo ``GradientBucket``.  Returns (bucket, kind)."""
+    if (prefer_peer and dist.is_initialized() and dist.get_world_size(group) > 1
+            and torch.device(device).type == "cuda"):
+        try:
+            return PeerGradientBucket(P, M, device, group), "peer"
+        except Exception as ex:      # no P2P / symmetric memory on this system: say so, use NCCL
+            import warnings
+            warnings.warn(f"symmetric-memory bucket unavailable ({ex!r}); falling back to the NCCL all-reduce")
+    return GradientBucket(P, M, device), "nccl"
+
+
 def shard_views(num_views: int, rank: int, world_size: int):
     """Indices of the views rank ``rank`` renders this step: view v goes to rank v % N."""
     return list(range(rank, num_views, world_size))

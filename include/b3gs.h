@@ -342,6 +342,21 @@ B3GS_API size_t b3gs_dist_cuda2_scratch_bytes(int P);
 B3GS_API int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes,
                              void* stream);
 
+/*
+ * ---- the data-parallel exchange over NVLink peer memory -------------
+ * In-place two-shot all-reduce (sum, then * scale) of one float buffer per rank that lives in
+ * symmetric memory: peer_buffers[r] is the device pointer of rank r's buffer as mapped into
+ * THIS process (torch.distributed._symmetric_memory buffer_ptrs), all 16-byte aligned and
+ * n_floats (a multiple of 4) long.  Rank `rank` reduces the rank-th slice and stores the
+ * result into every peer's buffer; all ranks must call it, bracketed by a cross-rank
+ * barrier on the same stream before (the peers' producers have finished) and after (the
+ * results have landed).  Every element is summed by exactly one rank in rank order, so all
+ * replicas end up bit-identical.
+ */
+#define B3GS_MAX_PEERS 8
+B3GS_API int b3gs_peer_allreduce(int world, int rank, float* const* peer_buffers, size_t n_floats, float scale,
+                                 void* stream);
+
 /* The composite backward exists in three shapes — 1, 2 or 4 pixels per lane (8x4, 8x8, 16x8
  * pixels per warp) — with identical results up to float summation order; n = 0 (default)
  * picks per call from the instances-per-Gaussian ratio, n = 1|2|4 forces one (tests, A/B
