@@ -29,23 +29,88 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const __grid_consta
     // this rank's slice of float4 indices
     const size_t per = (n4 + N - 1) / N;
     const size_t lo = per * rank, hi = lo + per < n4 ? lo + per : n4;
+    // kUnroll float4s per thread and iteration: N * kUnroll independent 16-byte NVLink loads in
+    // flight per thread before the first add (remote latency is ~2 us)
+    constexpr int kUnroll = N <= 2 ? 4 : 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-        float4 v[N];
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t base = lo + t0; base < hi; base += stride * kUnroll) {
+        float4 v[kUnroll][N];
 #pragma unroll
-        for (int r = 0; r < N; r++) v[r] = __ldcg(reinterpret_cast<const float4*>(peers.p[r]) + i);  // L2 only: peer data
-        float4 s = v[0];
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * stride;
 #pragma unroll
-        for (int r = 1; r < N; r++) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
-        s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+            for (int r = 0; r < N; r++)
+                v[u][r] = i < hi ? __ldcg(reinterpret_cast<const float4*>(peers.p[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int r = 0; r < N; r++) __stcg(reinterpret_cast<float4*>(peers.p[r]) + i, s);
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * stride;
+            if (i >= hi) break;
+            float4 s = v[u][0];
+#pragma unroll
+            for (int r = 1; r < N; r++) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
+            s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+#pragma unroll
+            for (int r = 0; r < N; r++) __stcg(reinterpret_cast<float4*>(peers.p[r]) + i, s);
+        }
+    }
+}
+
+// NVLS variant: `mc` is the MULTICAST address of the same symmetric buffer
+// (cuMulticast / NVSwitch).  multimem.ld_reduce returns the sum over all ranks' copies,
+// formed inside the switch (one NVLink read instead of N-1), multimem.st broadcasts the
+// result to all of them (one write instead of N-1).  The summation order inside the switch is
+// unspecified, but every element is still reduced exactly once and then broadcast, so the
+// replicas stay bit-identical.
+__global__ void __launch_bounds__(256) peer_allreduce_multimem_kernel(float* mc, int world, int rank, size_t n4,
+                                                                     float scale) {
+    const size_t per = (n4 + world - 1) / world;
+    const size_t lo = per * rank, hi = lo + per < n4 ? lo + per : n4;
+    constexpr int kUnroll = 4;  // independent switch reductions in flight per thread
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * kUnroll) {
+        float4 s[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * stride;
+            s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(s[u].x), "=f"(s[u].y), "=f"(s[u].z), "=f"(s[u].w)
+                             : "l"(mc + 4 * i)
+                             : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+            const size_t i = base + u * stride;
+            if (i >= hi) break;
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i),
+                         "f"(s[u].x * scale), "f"(s[u].y * scale), "f"(s[u].z * scale), "f"(s[u].w * scale)
+                         : "memory");
+        }
     }
 }
 
 }  // namespace b3
 
 using namespace b3;
+
+extern "C" int b3gs_peer_allreduce_multimem(int world, int rank, float* multicast_buffer, size_t n_floats, float scale,
+                                            void* stream) {
+    if (world < 1 || rank < 0 || rank >= world || !multicast_buffer || (n_floats & 3) ||
+        (reinterpret_cast<uintptr_t>(multicast_buffer) & 15))
+        return -1;
+    const size_t n4 = n_floats / 4;
+    if (n4 == 0) return 0;
+    size_t blocks = ((n4 + world - 1) / world + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    peer_allreduce_multimem_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        multicast_buffer, world, rank, n4, scale);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int b3gs_peer_allreduce(int world, int rank, float* const* peer_buffers, size_t n_floats, float scale,
                                    void* stream) {
@@ -59,7 +124,7 @@ extern "C" int b3gs_peer_allreduce(int world, int rank, float* const* peer_buffe
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // one slice per rank: size the grid for the slice, capped at 148 SMs x 8 blocks
     size_t blocks = ((n4 + world - 1) / world + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     switch (world) {
         case 1: peer_allreduce_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(pp, rank, n4, scale); break;

@@ -100,6 +100,22 @@ class PeerGradientBucket(GradientBucket):
         self._fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t,
                              ctypes.c_float, ctypes.c_void_p]
         self._fn.restype = ctypes.c_int
+        # NVLS: reduce inside the NVSwitch when the buffer has a multicast mapping
+        # (B3GS_DP_MULTIMEM=0 keeps the plain peer loads/stores)
+        import os
+        self._mc_ptr = 0
+        # measured on 8x B200 (18.4 MB bucket): multimem 70 us, plain peer 74 us, NCCL 108 us; on
+        # 2x B200: multimem 66 us, plain 46 us, NCCL 64 us -> the switch reduction from 4 ranks up
+        mm = os.environ.get("B3GS_DP_MULTIMEM", "auto")
+        if mm == "1" or (mm == "auto" and self.world >= 4):
+            try:
+                self._mc_ptr = int(self._handle.multicast_ptr or 0)     # 0 when the system has no NVLS
+            except Exception:
+                self._mc_ptr = 0
+        self._fn_mc = _backend.native().lib.b3gs_peer_allreduce_multimem
+        self._fn_mc.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float,
+                                ctypes.c_void_p]
+        self._fn_mc.restype = ctypes.c_int
         off = 0
         for name in SEGMENTS:
             cnt = self.P * self.widths[name]
@@ -116,8 +132,11 @@ class PeerGradientBucket(GradientBucket):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._handle.barrier(channel=0)        # every peer's backward has written its bucket
-            rc = self._fn(self.world, self.rank, self._ptrs, self.flat.numel(),
-                          (1.0 / self.world) if average else 1.0, stream)
+            scale = (1.0 / self.world) if average else 1.0
+            if self._mc_ptr:
+                rc = self._fn_mc(self.world, self.rank, self._mc_ptr, self.flat.numel(), scale, stream)
+            else:
+                rc = self._fn(self.world, self.rank, self._ptrs, self.flat.numel(), scale, stream)
             if rc != 0:
                 raise RuntimeError(f"b3gs_peer_allreduce failed ({rc})")
             self._handle.barrier(channel=1)        # every peer's slice has landed everywhere

@@ -356,6 +356,12 @@ B3GS_API int b3gs_dist_cuda2(int P, const float* points, float* mean_dist2, void
 #define B3GS_MAX_PEERS 8
 B3GS_API int b3gs_peer_allreduce(int world, int rank, float* const* peer_buffers, size_t n_floats, float scale,
                                  void* stream);
+/* The same exchange through the NVSwitch (NVLS): multicast_buffer is the multicast address of
+ * the symmetric buffer (_SymmetricMemory.multicast_ptr); the sum is formed inside the switch by
+ * multimem.ld_reduce and broadcast by multimem.st.  Same calling protocol (barrier before and
+ * after); replicas bit-identical, summation order unspecified. */
+B3GS_API int b3gs_peer_allreduce_multimem(int world, int rank, float* multicast_buffer, size_t n_floats,
+                                          float scale, void* stream);
 
 /* The composite backward exists in three shapes — 1, 2 or 4 pixels per lane (8x4, 8x8, 16x8
  * pixels per warp) — with identical results up to float summation order; n = 0 (default)

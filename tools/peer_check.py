@@ -55,7 +55,14 @@ for P, M in ((1001, 4), (200_000, 4), (300_001, 16)):
         return float(t)
     t_peer = time_it(lambda: peer.all_reduce(average=True))
     t_nccl = time_it(lambda: ref.all_reduce(average=True))
+    mc = bool(peer._mc_ptr)
+    t_plain = t_peer
+    if mc:      # also time the plain peer load/store kernel
+        keep, peer._mc_ptr = peer._mc_ptr, 0
+        t_plain = time_it(lambda: peer.all_reduce(average=True))
+        peer._mc_ptr = keep
     if rank == 0:
-        print("P=%d M=%d (%.1f MB) world=%d: rel diff vs NCCL %.2e, replicas bit-identical; peer %.1f us, NCCL %.1f us"
-              % (P, M, peer.nbytes / 1e6, world, worst, t_peer * 1e3, t_nccl * 1e3), flush=True)
+        print("P=%d M=%d (%.1f MB) world=%d: rel diff vs NCCL %.2e, replicas bit-identical; %s %.1f us, plain peer %.1f us, "
+              "NCCL %.1f us" % (P, M, peer.nbytes / 1e6, world, worst, "multimem" if mc else "peer", t_peer * 1e3,
+                                t_plain * 1e3, t_nccl * 1e3), flush=True)
 dist.destroy_process_group()
