@@ -398,14 +398,29 @@ def main():
             next_rows["parameter_plumbing"] = bench_params.measure(dev, P, M)
         except Exception as ex:
             next_rows["parameter_plumbing"] = {"error": repr(ex)}
+        # The native arm never executes anything under oracle/: the reference's own kernels
+        # for these two rows are timed by `bench.py --impl reference` (same keys, below).
         try:  # §8(f) rank 4 on an SfM-like cloud
             import bench_knn
-            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3)
+            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3, which="native")
         except Exception as ex:
             next_rows["dist_cuda2"] = {"error": repr(ex)}
         try:  # everything together: the reference's training iteration on the binocular config
             import bench_iteration
-            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5)
+            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5, which=("native",))
+        except Exception as ex:
+            next_rows["train_iteration"] = {"error": repr(ex)}
+    elif rank == 0 and world == 1 and args.impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        next_rows = {}
+        try:  # the reference's simple-knn kernel (oracle/_ref/libknn_ref.so) on the same cloud
+            import bench_knn
+            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3, which="reference")
+        except Exception as ex:
+            next_rows["dist_cuda2"] = {"error": repr(ex)}
+        try:  # the reference's kernels + everything around them as the reference writes it
+            import bench_iteration
+            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5, which=("reference_style",))
         except Exception as ex:
             next_rows["train_iteration"] = {"error": repr(ex)}
 

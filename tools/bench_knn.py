@@ -17,10 +17,12 @@ mkg = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mkg)
 
 
-def measure(P=1_000_000, kind="clustered", iters=5):
+def measure(P=1_000_000, kind="clustered", iters=5, which="both"):
+    """which: "native" (this library only; nothing under oracle/ is touched), "reference" (the
+    reference's kernel only) or "both" (A/B with a bit-identity check)."""
     from simple_knn._C import distCUDA2
     pts = mkg.make_points(P, kind, 1).cuda()
-    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libknn_ref.so"))
+    have_ref = which != "native" and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libknn_ref.so"))
 
     def wall(fn):
         best = 1e9
@@ -31,13 +33,17 @@ def measure(P=1_000_000, kind="clustered", iters=5):
             torch.cuda.synchronize()
             best = min(best, time.perf_counter() - t0)
         return best * 1e3, out
-    distCUDA2(pts)
-    t_new, a = wall(distCUDA2)
-    res = {"what": "distCUDA2, %d points (%s)" % (P, kind), "native_ms": round(t_new, 3)}
+    res = {"what": "distCUDA2, %d points (%s)" % (P, kind)}
+    if which != "reference":
+        distCUDA2(pts)
+        t_new, a = wall(distCUDA2)
+        res["native_ms"] = round(t_new, 3)
     if have_ref:
         mkg.reference_dist_cuda2(pts)
         t_ref, b = wall(mkg.reference_dist_cuda2)
-        res.update(reference_kernel_ms=round(t_ref, 3), speedup=round(t_ref / t_new, 2), bit_identical=bool(torch.equal(a, b)))
+        res["reference_kernel_ms"] = round(t_ref, 3)
+        if which == "both":
+            res.update(speedup=round(t_ref / t_new, 2), bit_identical=bool(torch.equal(a, b)))
     return res
 
 
