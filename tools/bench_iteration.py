@@ -10,7 +10,8 @@ timed two ways on the same GPU:
                    (gaussian_model.py:409-411) and torch.optim.Adam.
   native           this library for every one of those rows: rasterizer (§8 a), fused
                    photometric loss (f1), fused binocular loss (f2), fused activations,
-                   densification statistics and one-launch Adam (f3).
+                   densification statistics and one-launch Adam (f3); the activations are
+                   evaluated once per iteration for both views of the pair.
 
 An iteration = render the training view + render the shifted view (binocular pair,
 train.py:122-127) + losses + backward + densification statistics + optimizer step,
@@ -75,11 +76,11 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
         opt = adam_cls([{"params": [params[k]], "lr": LRS[k], "name": k} for k in ORDER], lr=0.0, eps=1e-15)
         accum, denom, max_radii = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, device=dev)
 
-        def render(camera):
+        def render(camera, acts=None):
             screenspace = torch.zeros_like(params["xyz"], requires_grad=True)
             if style == "native":
-                shs, opacity, scales, rotations = parameters.activate(params["f_dc"], params["f_rest"], params["opacity"],
-                                                                      params["scaling"], params["rotation"])
+                # both views of the pair see the same parameters: activate once per iteration
+                shs, opacity, scales, rotations = acts
             else:
                 shs = torch.cat((params["f_dc"], params["f_rest"]), dim=1)
                 opacity, scales = torch.sigmoid(params["opacity"]), torch.exp(params["scaling"])
@@ -94,8 +95,12 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
             return image, radii, depth, screenspace
 
         def iteration():
-            image, radii, depth, screenspace = render(cam)
-            shifted_image = render(cam_shift)[0]
+            acts = None
+            if style == "native":
+                acts = parameters.activate(params["f_dc"], params["f_rest"], params["opacity"], params["scaling"],
+                                           params["rotation"])
+            image, radii, depth, screenspace = render(cam, acts)
+            shifted_image = render(cam_shift, acts)[0]
             if style == "native":
                 disparity_loss = binocular.binocular_consistency_loss(shifted_image, depth, gt, focal_x, trans_dist)
                 loss = losses.photometric_loss(image, gt, 0.2)
