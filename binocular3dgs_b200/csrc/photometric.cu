@@ -43,17 +43,24 @@ __constant__ float kGauss[kWin] = {0.001028380123898387f,  0.0075987582094967365
                                    0.21300552785396576f,   0.10936068743467331f,   0.036000773310661316f,
                                    0.0075987582094967365f, 0.001028380123898387f};
 
-// out[i] = sum_k w[k] * in[i + k], i < 8
-__device__ __forceinline__ void conv8(const float (&in)[kSegIn], float (&out)[kSeg]) {
+// out[i] = sum_k w[k] * in[i + k], i < SEG
+template <int SEG>
+__device__ __forceinline__ void conv_seg(const float (&in)[SEG + kWin - 1], float (&out)[SEG]) {
 #pragma unroll
-    for (int i = 0; i < kSeg; i++) out[i] = 0.f;
+    for (int i = 0; i < SEG; i++) out[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < kWin; k++) {
         const float w = kGauss[k];
 #pragma unroll
-        for (int i = 0; i < kSeg; i++) out[i] = fmaf(w, in[i + k], out[i]);
+        for (int i = 0; i < SEG; i++) out[i] = fmaf(w, in[i + k], out[i]);
     }
 }
+__device__ __forceinline__ void conv8(const float (&in)[kSegIn], float (&out)[kSeg]) { conv_seg<kSeg>(in, out); }
+
+// The vertical pass uses segments of 4 outputs (14 inputs) so that 32 columns x 8 segments
+// occupy all 256 threads (8-output segments would leave half the block idle in that phase).
+constexpr int kVSeg = 4, kVSegIn = kVSeg + kWin - 1, kVSegs = kTile / kVSeg;
+static_assert(kTile * kVSegs == kThreads, "vertical pass: one work item per thread");
 
 // Stage the 42x42 halo of one image plane into shared memory (zero padding == conv2d
 // padding=5).  When rows are 16-byte aligned (W % 4 == 0 and an aligned base) the halo is
@@ -157,29 +164,29 @@ __global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
         for (int i = 0; i < kSeg; i++) h[4][r][sx + i] = o[i];
     }
     __syncthreads();
-    // vertical pass: 32 columns x 4 segments of 8 outputs (threads 0..127), then the SSIM map
+    // vertical pass: 32 columns x 8 segments of 4 outputs (all 256 threads), then the SSIM map
     float ssim_sum = 0.f, l1_sum = 0.f;
-    if (tid < kTile * kSegs) {
-        const int lx = tid & (kTile - 1), sy = (tid / kTile) * kSeg;
-        float in[kSegIn], mu1[kSeg], mu2[kSeg], e11[kSeg], e22[kSeg], e12[kSeg];
+    {
+        const int lx = tid & (kTile - 1), sy = (tid / kTile) * kVSeg;
+        float in[kVSegIn], mu1[kVSeg], mu2[kVSeg], e11[kVSeg], e22[kVSeg], e12[kVSeg];
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) in[j] = h[0][sy + j][lx];
-        conv8(in, mu1);
+        for (int j = 0; j < kVSegIn; j++) in[j] = h[0][sy + j][lx];
+        conv_seg<kVSeg>(in, mu1);
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) in[j] = h[1][sy + j][lx];
-        conv8(in, mu2);
+        for (int j = 0; j < kVSegIn; j++) in[j] = h[1][sy + j][lx];
+        conv_seg<kVSeg>(in, mu2);
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) in[j] = h[2][sy + j][lx];
-        conv8(in, e11);
+        for (int j = 0; j < kVSegIn; j++) in[j] = h[2][sy + j][lx];
+        conv_seg<kVSeg>(in, e11);
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) in[j] = h[3][sy + j][lx];
-        conv8(in, e22);
+        for (int j = 0; j < kVSegIn; j++) in[j] = h[3][sy + j][lx];
+        conv_seg<kVSeg>(in, e22);
 #pragma unroll
-        for (int j = 0; j < kSegIn; j++) in[j] = h[4][sy + j][lx];
-        conv8(in, e12);
+        for (int j = 0; j < kVSegIn; j++) in[j] = h[4][sy + j][lx];
+        conv_seg<kVSeg>(in, e12);
         const int gx = x0 + lx;
 #pragma unroll
-        for (int i = 0; i < kSeg; i++) {
+        for (int i = 0; i < kVSeg; i++) {
             const int gy = y0 + sy + i;
             if (gx < W && gy < H) {
                 const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) photometric_forward_kernel(
     if (tid == 0) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int w = 0; w < kTile * kSegs / 32; w++) { a += s_red[0][w]; b += s_red[1][w]; }
+        for (int w = 0; w < kThreads / 32; w++) { a += s_red[0][w]; b += s_red[1][w]; }
         finish_sums(sums, a, b, gridDim.x * gridDim.y * gridDim.z, k0, k1, k2, loss_out);
     }
 }
@@ -244,23 +251,22 @@ __global__ void __launch_bounds__(kThreads) photometric_backward_kernel(
         }
     }
     __syncthreads();
-    if (tid >= kTile * kSegs) return;
-    const int lx = tid & (kTile - 1), sy = (tid / kTile) * kSeg;
-    float in[kSegIn], a[kSeg], b[kSeg], d[kSeg];
+    const int lx = tid & (kTile - 1), sy = (tid / kTile) * kVSeg;
+    float in[kVSegIn], a[kVSeg], b[kVSeg], d[kVSeg];
 #pragma unroll
-    for (int j = 0; j < kSegIn; j++) in[j] = h[0][sy + j][lx];
-    conv8(in, a);
+    for (int j = 0; j < kVSegIn; j++) in[j] = h[0][sy + j][lx];
+    conv_seg<kVSeg>(in, a);
 #pragma unroll
-    for (int j = 0; j < kSegIn; j++) in[j] = h[1][sy + j][lx];
-    conv8(in, b);
+    for (int j = 0; j < kVSegIn; j++) in[j] = h[1][sy + j][lx];
+    conv_seg<kVSeg>(in, b);
 #pragma unroll
-    for (int j = 0; j < kSegIn; j++) in[j] = h[2][sy + j][lx];
-    conv8(in, d);
+    for (int j = 0; j < kVSegIn; j++) in[j] = h[2][sy + j][lx];
+    conv_seg<kVSeg>(in, d);
     const int gx = x0 + lx;
     if (gx >= W) return;
     const float g = upstream[0], gS = g * k_ssim, gL1 = g * k_l1;
 #pragma unroll
-    for (int i = 0; i < kSeg; i++) {
+    for (int i = 0; i < kVSeg; i++) {
         const int gy = y0 + sy + i;
         if (gy >= H) break;
         const size_t o = c * plane + (size_t)gy * W + gx;
