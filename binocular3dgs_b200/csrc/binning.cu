@@ -144,7 +144,12 @@ static void exclusive_scan_gather(const uint32_t* in, const uint32_t* idx, uint3
 // ------------------------------------------------------------------ radix pass (8-bit digits)
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
-constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
+constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block (R-sized passes)
+// The P-sized depth sort is latency-bound: with 8 keys per thread it has twice the blocks
+// (98 at 200k Gaussians instead of 49 on 148 SMs): lego 60.8 -> 49.2 us, fern 69.8 -> 51.5.
+// The R-sized tile sort keeps 16 (half the histogram table; dtu 0.667 vs 0.726 ms with 8).
+constexpr int kDepthItems = 8;
+constexpr int kDepthTile = kRadixThreads * kDepthItems;  // 2048
 constexpr int kRadixBins = 256;
 
 static int radix_blocks(int n) { return (n + kRadixTile - 1) / kRadixTile; }
@@ -158,23 +163,24 @@ __device__ __forceinline__ T ld_u32(const T* p) {
 
 // KeyT is uint32_t for the depth sort and uint16_t for the tile sort (tile ids < 65536:
 // 6 instead of 8 bytes per instance and pass).
-template <typename KeyT>
+template <typename KeyT, int kItems = kRadixItems>
 struct RadixSmemT {
     uint32_t warp_cnt[kRadixThreads / 32][kRadixBins];  // 8 KB
     uint32_t global_base[kRadixBins];
     uint32_t block_start[kRadixBins];
     uint32_t scan[32];
-    KeyT keys[kRadixTile];      // 16 or 8 KB
-    uint32_t vals[kRadixTile];  // 16 KB
+    KeyT keys[kRadixThreads * kItems];      // 16 or 8 KB at 16 items
+    uint32_t vals[kRadixThreads * kItems];  // 16 KB
 };
 typedef RadixSmemT<uint32_t> RadixSmem;
 
 // hist[d * nb + tile] = number of keys of `tile` with digit d.  s_cnt: 256 words.
-template <bool kCoop, typename KeyT>
+template <bool kCoop, typename KeyT, int kItems = kRadixItems>
 __device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const KeyT* __restrict__ keys, int n,
                                                 int shift, uint32_t* __restrict__ hist, int nb) {
-    const int base = tile * kRadixTile;
-    if (!kCoop && sizeof(KeyT) == 2 && base + kRadixTile <= n) {
+    constexpr int kTileN = kRadixThreads * kItems;
+    const int base = tile * kTileN;
+    if (!kCoop && sizeof(KeyT) == 2 && kItems == 16 && base + kTileN <= n) {
         // full tile of 16-bit keys: 16 consecutive keys per thread as two 16-byte loads (a
         // histogram does not care which thread sees which key)
         const uint4* p = reinterpret_cast<const uint4*>(keys + base) + 2 * threadIdx.x;
@@ -193,16 +199,16 @@ __device__ __forceinline__ void radix_hist_tile(uint32_t* s_cnt, int tile, const
         return;
     }
     // all 16 loads in flight before the first shared atomic (one memory round trip)
-    uint32_t k[kRadixItems];
+    uint32_t k[kItems];
 #pragma unroll
-    for (int i = 0; i < kRadixItems; i++) {
+    for (int i = 0; i < kItems; i++) {
         const int j = base + i * kRadixThreads + threadIdx.x;
         k[i] = j < n ? (uint32_t)ld_u32<kCoop>(keys + j) : 0u;
     }
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kRadixItems; i++) {
+    for (int i = 0; i < kItems; i++) {
         const int j = base + i * kRadixThreads + threadIdx.x;
         if (j < n) atomicAdd(&s_cnt[(k[i] >> shift) & 0xffu], 1u);
     }
@@ -285,23 +291,24 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
 // Stable rank-and-scatter of one 4096-key tile.  kIota: values are the key indices.
 // kPreloaded: the caller already put the digit totals in sm.block_start[] and the
 // same-digit-earlier-tiles prefix in sm.global_base[] (cooperative in-block-prefix path).
-template <bool kIota, bool kCoop, bool kPreloaded, typename KeyT>
-__device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT>& sm, int tile, const KeyT* __restrict__ keys_in,
+template <bool kIota, bool kCoop, bool kPreloaded, typename KeyT, int kItems = kRadixItems>
+__device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT, kItems>& sm, int tile, const KeyT* __restrict__ keys_in,
                                                    const uint32_t* __restrict__ vals_in,
                                                    KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                    const uint32_t* __restrict__ hist_scanned,
                                                    const uint32_t* __restrict__ digit_totals, int n, int shift,
                                                    int nb) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int base = tile * kRadixTile;
+    constexpr int kTileN = kRadixThreads * kItems;
+    const int base = tile * kTileN;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     // issue every global load of the tile first (one memory round trip), then rank
-    uint32_t k[kRadixItems], v[kRadixItems];
-    uint32_t rank2[kRadixItems / 2];  // two 16-bit ranks per register (rank < 4096)
+    uint32_t k[kItems], v[kItems];
+    uint32_t rank2[kItems / 2];  // two 16-bit ranks per register (rank < 4096)
 #pragma unroll
-    for (int r = 0; r < kRadixItems; r++) {
-        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
+    for (int r = 0; r < kItems; r++) {
+        const int j = base + warp * (32 * kItems) + r * 32 + lane;  // warp-striped: order = (warp, r, lane)
         const bool valid = j < n;
         k[r] = valid ? (uint32_t)ld_u32<kCoop>(keys_in + j) : 0xffffffffu;
         v[r] = valid ? (kIota ? (uint32_t)j : ld_u32<kCoop>(vals_in + j)) : 0u;
@@ -318,8 +325,8 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT>& sm, int til
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kRadixItems; r++) {
-        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;
+    for (int r = 0; r < kItems; r++) {
+        const int j = base + warp * (32 * kItems) + r * 32 + lane;
         // out-of-range slots sit at the very end of the tile and carry digit 255, so they
         // rank after every real key and are simply not written back.
         const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
@@ -347,8 +354,8 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT>& sm, int til
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kRadixItems; r++) {
-        const int j = base + warp * (32 * kRadixItems) + r * 32 + lane;
+    for (int r = 0; r < kItems; r++) {
+        const int j = base + warp * (32 * kItems) + r * 32 + lane;
         const uint32_t d = (j < n) ? ((k[r] >> shift) & 0xffu) : 0xffu;
         const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
         const uint32_t pos = sm.block_start[d] + sm.warp_cnt[warp][d] + rk;
@@ -356,7 +363,7 @@ __device__ __forceinline__ void radix_scatter_tile(RadixSmemT<KeyT>& sm, int til
         sm.vals[pos] = v[r];
     }
     __syncthreads();
-    const int nvalid = min(kRadixTile, n - base);
+    const int nvalid = min(kTileN, n - base);
     for (int i = tid; i < nvalid; i += kRadixThreads) {
         const uint32_t key = sm.keys[i];
         const uint32_t d = (key >> shift) & 0xffu;
@@ -450,13 +457,13 @@ struct Phase1Args {
 // Up to this many radix tiles each block derives its own offsets straight from the
 // tile-major histogram (one coalesced column walk) instead of a separate row-scan phase
 // and its grid barrier.
-constexpr int kInBlockPrefixMaxTiles = 128;
+constexpr int kInBlockPrefixMaxTiles = 256;
 
 __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a) {
-    __shared__ RadixSmem sm;
+    __shared__ RadixSmemT<uint32_t, kDepthItems> sm;
     cg::grid_group grid = cg::this_grid();
     const int n = a.P;
-    const int nb = (n + kRadixTile - 1) / kRadixTile;
+    const int nb = (n + kDepthTile - 1) / kDepthTile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Bytes in which every visible key agrees need no pass.  (Invisible Gaussians carry
     // key 0 and may end up anywhere: they emit no instances.)
@@ -480,17 +487,17 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
         if (in_block_prefix) {
             // tile-major histogram: hist[tile * 256 + digit]
             for (int t = blockIdx.x; t < nb; t += gridDim.x) {
-                const int base = t * kRadixTile;
-                uint32_t kk[kRadixItems];
+                const int base = t * kDepthTile;
+                uint32_t kk[kDepthItems];
 #pragma unroll
-                for (int i = 0; i < kRadixItems; i++) {
+                for (int i = 0; i < kDepthItems; i++) {
                     const int j = base + i * kRadixThreads + tid;
                     kk[i] = j < n ? __ldcg(kin + j) : 0u;
                 }
                 sm.global_base[tid] = 0;
                 __syncthreads();
 #pragma unroll
-                for (int i = 0; i < kRadixItems; i++) {
+                for (int i = 0; i < kDepthItems; i++) {
                     const int j = base + i * kRadixThreads + tid;
                     if (j < n) atomicAdd(&sm.global_base[(kk[i] >> shift) & 0xffu], 1u);
                 }
@@ -512,14 +519,14 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
                 sm.global_base[tid] = before;    // same digit, earlier tiles
                 __syncthreads();
                 if (first)
-                    radix_scatter_tile<true, true, true, uint32_t>(sm, t, kin, nullptr, kout, vout, nullptr, nullptr, n, shift, nb);
+                    radix_scatter_tile<true, true, true, uint32_t, kDepthItems>(sm, t, kin, nullptr, kout, vout, nullptr, nullptr, n, shift, nb);
                 else
-                    radix_scatter_tile<false, true, true, uint32_t>(sm, t, kin, vin, kout, vout, nullptr, nullptr, n, shift, nb);
+                    radix_scatter_tile<false, true, true, uint32_t, kDepthItems>(sm, t, kin, vin, kout, vout, nullptr, nullptr, n, shift, nb);
             }
             grid.sync();
         } else {
             for (int t = blockIdx.x; t < nb; t += gridDim.x)
-                radix_hist_tile<true, uint32_t>(sm.global_base, t, kin, n, shift, a.hist, nb);
+                radix_hist_tile<true, uint32_t, kDepthItems>(sm.global_base, t, kin, n, shift, a.hist, nb);
             grid.sync();
             // row scan: one warp per digit row
             for (int row = blockIdx.x * (kRadixThreads / 32) + warp; row < kRadixBins;
@@ -538,9 +545,9 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
             grid.sync();
             for (int t = blockIdx.x; t < nb; t += gridDim.x) {
                 if (first)
-                    radix_scatter_tile<true, true, false, uint32_t>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
+                    radix_scatter_tile<true, true, false, uint32_t, kDepthItems>(sm, t, kin, nullptr, kout, vout, a.hist, a.totals, n, shift, nb);
                 else
-                    radix_scatter_tile<false, true, false, uint32_t>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
+                    radix_scatter_tile<false, true, false, uint32_t, kDepthItems>(sm, t, kin, vin, kout, vout, a.hist, a.totals, n, shift, nb);
             }
             grid.sync();
         }
@@ -598,9 +605,14 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
 }
 
 // scratch layout (u32 elements): keysA[P] keysB[P] valsA[P] valsB[P] hist[...] scan_sums[...]
+static int depth_blocks(int n) { return (n + kDepthTile - 1) / kDepthTile; }
+// histogram scratch of phase 1: the larger of the cooperative (2048-key blocks) and the
+// multi-kernel fallback (4096-key blocks) layouts
+static size_t depth_scratch_elems(int n) { return (size_t)kRadixBins * depth_blocks(n) + kRadixBins; }
+
 size_t binning_phase1_scratch_bytes(int P) {
     const size_t p = (size_t)(P > 0 ? P : 0);
-    return (align_up(p * 4, 256) * 4 + align_up(radix_scratch_elems(P) * 4, 256) +
+    return (align_up(p * 4, 256) * 4 + align_up(depth_scratch_elems(P) * 4, 256) +
             align_up((scan_tiles(P) + 1) * 4, 256));
 }
 
@@ -630,19 +642,19 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
     uint32_t* keysC = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
     uint32_t* valsA = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
     uint32_t* valsB = reinterpret_cast<uint32_t*>(q); q += align_up(p * 4, 256);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(q);  q += align_up(radix_scratch_elems(a.P) * 4, 256);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(q);  q += align_up(depth_scratch_elems(a.P) * 4, 256);
     uint32_t* sums = reinterpret_cast<uint32_t*>(q);
-    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.P);
+    uint32_t* totals = hist + (size_t)kRadixBins * radix_blocks(a.P);   // multi-kernel fallback layout
     const uint32_t* dkeys = reinterpret_cast<const uint32_t*>(a.depths);
     const int limit = coop_grid_limit();
     if (limit > 0) {
         Phase1Args k;
         k.P = a.P; k.dkeys = dkeys; k.tiles_touched = a.tiles_touched; k.key_bits = a.key_bits;
         k.keysB = keysB; k.keysC = keysC; k.valsA = valsA; k.valsB = valsB;
-        k.hist = hist; k.totals = totals; k.sums = sums;
+        k.hist = hist; k.totals = hist + (size_t)kRadixBins * depth_blocks(a.P); k.sums = sums;
         k.sorted_ids = a.sorted_ids; k.sorted_offsets = a.sorted_offsets;
         // at least 32 blocks so that the 256 digit rows find 256 warps
-        int grid = radix_blocks(a.P) < 32 ? 32 : radix_blocks(a.P);
+        int grid = depth_blocks(a.P) < 32 ? 32 : depth_blocks(a.P);
         if (grid > limit) grid = limit;
         void* args[] = {&k};
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)depth_sort_coop, dim3(grid), dim3(kRadixThreads), args,
