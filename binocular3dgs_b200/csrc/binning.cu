@@ -146,7 +146,8 @@ constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block (R-sized passes)
 // The P-sized depth sort is latency-bound: with 8 keys per thread it has twice the blocks
-// (98 at 200k Gaussians instead of 49 on 148 SMs): lego 60.8 -> 49.2 us, fern 69.8 -> 51.5.
+// (98 at 200k Gaussians instead of 49 on 148 SMs): lego 60.8 -> 48.8 us, fern 69.8 -> 51.3
+// (4 keys per thread: 60.1 / 75.4 us — the per-block prefix walk over all blocks takes over).
 // The R-sized tile sort keeps 16 (half the histogram table; dtu 0.667 vs 0.726 ms with 8).
 constexpr int kDepthItems = 8;
 constexpr int kDepthTile = kRadixThreads * kDepthItems;  // 2048
