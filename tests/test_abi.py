@@ -73,3 +73,22 @@ def test_cpu_tensor_is_rejected_not_silently_computed():
     with pytest.raises(RuntimeError, match="CUDA"):
         r(means3D=torch.zeros(4, 3), means2D=torch.zeros(4, 3), opacities=torch.ones(4, 1),
           colors_precomp=torch.ones(4, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (nor the drop-in module
+    shims) may import, load or execute it — the product path has no CPU / reference fallback."""
+    import glob
+    offenders = []
+    files = (glob.glob(os.path.join(ROOT, "binocular3dgs_b200", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(ROOT, "binocular3dgs_b200", "csrc", "*.c*"))
+             + glob.glob(os.path.join(ROOT, "diff_gaussian_rasterization", "*.py"))
+             + glob.glob(os.path.join(ROOT, "simple_knn", "*.py")))
+    assert len(files) > 15
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#include\s+\".*oracle)|liboracle|libdgr_ref|libknn_ref|_ref/")
+    for f in files:
+        for i, line in enumerate(open(f, errors="replace"), 1):
+            if pat.search(line) and "oracle/refbackend.py" not in line and not line.lstrip().startswith(("#", "//", "*", '"'))\
+                    and "``oracle" not in line:
+                offenders.append((os.path.relpath(f, ROOT), i, line.strip()))
+    assert not offenders, offenders
