@@ -103,3 +103,12 @@ def test_peer_all_reduce_matches_nccl_on_two_gpus():
                           os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("replicas bit-identical") == 3
+
+
+def test_make_bucket_without_cuda_is_the_plain_bucket():
+    """make_bucket only chooses the symmetric-memory bucket for CUDA devices inside an
+    initialised multi-rank group; everywhere else it is the plain (gloo / NCCL) bucket."""
+    from binocular3dgs_b200.dp import GradientBucket, make_bucket
+    b, kind = make_bucket(33, 4, "cpu")
+    assert kind == "nccl" and type(b) is GradientBucket
+    assert b.flat.numel() >= 33 * 23 and all((v.data_ptr() - b.flat.data_ptr()) % 16 == 0 for v in b.views().values())
