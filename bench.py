@@ -4,32 +4,44 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: under torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-One "step" = one view = one rasterizer forward + one backward over one batch of
-synthetic input (BASELINE.json configs[1]: ~200k Gaussians, 800x800, SH degree 1).
+One "step" = one pass of the hot path over one batch of synthetic input.  The default
+workload is BASELINE.json configs[3], the largest single-GPU configuration: DTU-sized,
+1 000 000 Gaussians at 1600x1200, one view (= one rasterizer forward + one backward) per
+step.  configs[1] (lego, 200k at 800x800) and configs[2]/[4] (LLFF fern binocular pair,
+300k at 1008x756, two renders per step, depth gradient on the first only —
+train.py:100,128,149) are measured in the same run and reported under "configs".
 
 What is timed
-  value   whole-job views/s with every input already resident in HBM: K steps, each
-          bracketed by CUDA events on the launch stream, an L2 flush (512 MiB memset)
-          between steps outside the event pairs, barrier + synchronize on both sides of
-          the region, MAX over ranks.  For N>1 every rank renders its own camera of the
-          replicated scene and the per-Gaussian gradients are summed by one NCCL
-          all-reduce of the flat bucket the backward kernel wrote into (inside the
-          step).  scaling = weak.
+  value   whole-job views/s with every input already resident in HBM, through the
+          `_C.rasterize_gaussians` / `_C.rasterize_gaussians_backward` pair (the C-ABI under
+          it): K steps, each bracketed by CUDA events on the launch stream, an L2 flush
+          (512 MiB memset) between steps outside the event pairs, barrier + synchronize on
+          both sides of the region, MAX over ranks.  For N>1 every rank renders its own
+          camera of the replicated scene and the per-Gaussian gradients are summed inside
+          the step by b3gs_peer_allreduce over NVLink peer memory (NCCL fallback).
+          scaling = weak.
   e2e     the same metric through the public API a user calls (GaussianRasterizer +
           autograd), with HOST buffers: each step copies that view's camera matrices and
           ground-truth image host->device from pinned memory, renders, takes an L1 loss,
           backpropagates to every Gaussian attribute and reads the loss back to the host.
   roofline  the dominant kernel (by measured device time) against the HBM peak in
-          MEASURED_PEAKS.json; algorithmic bytes from SURVEY.md §8(d).
+          MEASURED_PEAKS.json; algorithmic bytes from SURVEY.md §8(d) / DESIGN.md §5.
   cpu_baseline  the CPU oracle (oracle/liboracle.so, all host threads) on a bounded
-          sample of the same workload, rank 0 only.
+          sample of the same workload, rank 0 at N=1 only.
 
---impl reference runs the reference's OWN CUDA kernels (oracle/_ref/libdgr_ref.so,
-compiled unmodified from /root/reference) through identical host code on the same GPU:
-the reference has no CPU implementation of this path, and BASELINE.json's target is
-">= 2x the reference diff-gaussian-rasterization on 1x B200".  With N>1 the reference
-arm runs N independent replicas (its own multi-GPU story, script/run_llff.py) with no
-collective.
+--impl reference runs the UNMODIFIED reference: the stock `diff_gaussian_rasterization`
+package built by its own setup.py into baseline/_ref (baseline/build_reference.sh), i.e.
+its own __init__.py -> _C (ext.cpp) -> rasterize_points.cu -> cuda_rasterizer/*.cu on the
+same GPU, same workload, same loops.  That process never imports binocular3dgs_b200 and
+maps none of this repository's shared libraries (asserted, and reported in the line).  The
+reference has no CPU implementation of this path; BASELINE.json's target is ">= 2x the
+reference diff-gaussian-rasterization on 1x B200".  With N>1 the reference arm runs N
+independent replicas (its own multi-GPU story, script/run_llff.py) with no collective.
+
+--impl veneer (not run by the driver) is round 1's second arm: the reference's kernels
+compiled behind this repository's C-ABI (oracle/_ref/libdgr_ref.so) under this repository's
+host code — it isolates kernels from host code, and carries the reference-kernel numbers
+of the §8(f) rows.
 """
 import argparse
 import json
@@ -46,12 +58,11 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from binocular3dgs_b200.dp import GradientBucket, make_bucket  # noqa: E402
-from binocular3dgs_b200.rasterizer import GaussianRasterizationSettings, make_surface  # noqa: E402
-from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402  (pure torch/numpy)
 
 METRIC = "training views/sec (fwd+bwd raster)"
 UNIT = "views/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 # --------------------------------------------------------------------------- helpers
@@ -112,16 +123,184 @@ def tile_work(n_contrib_hw, W, H):
     return int(pad.view(gy, 16, gx, 16).amax(dim=(1, 3)).sum())
 
 
+def algorithmic_bytes(P, R, T, N, D, I_f):
+    """Algorithmic bytes per launch of each stage (adapted in DESIGN.md §5
+    where this library's algorithm moves fewer bytes than the reference's)."""
+    return {
+        "preprocess": P * (44 + 12 * (D + 1) ** 2) + 75 * P,
+        # 4 passes x (4 B hist read + 8 B read + 8 B write) + gather-scan of tiles_touched
+        "depth_sort": P * (4 * 20 + 16),
+        # emit (tile,id) 8 B + passes x 20 B + 4 B boundary scan per instance, 8 B per tile
+        "binning": 28 * P + R * (8 + 20 * (1 if T <= 256 else 2 if T <= 65536 else 3) + 4) + 8 * T,
+        "composite_forward": 44 * I_f + 8 * T + 24 * N,
+        "grad_zero": 48 * P,
+        "composite_backward": 44 * I_f + 8 * T + 28 * N + 80 * I_f,
+        "preprocess_backward": P * (111 + 12 * (D + 1) ** 2) + P * (40 + 12 * (D + 1) ** 2),
+    }
+
+
+def mapped_repo_libraries():
+    """Shared objects of THIS repository mapped into the process (/proc/self/maps)."""
+    libs = set()
+    try:
+        for line in open("/proc/self/maps"):
+            p = line.split()[-1]
+            if p.endswith(".so") and p.startswith(ROOT + os.sep):
+                libs.add(os.path.relpath(p, ROOT))
+    except OSError:
+        pass
+    return sorted(libs)
+
+
+# --------------------------------------------------------------------------- the arms
+class Arm:
+    """What a measurement loop needs from an implementation: the `_C`-level pair and the
+    public surface.  `C` exposes rasterize_gaussians / rasterize_gaussians_backward with
+    the reference's signatures (rasterize_points.h:18-65)."""
+    name = "?"
+    is_native = False
+    null_grads = False          # may dL/ddepth and dL/dalpha travel as None?
+    C = None
+    GaussianRasterizer = None
+    GaussianRasterizationSettings = None
+    describe = ""
+
+
+def load_native():
+    import binocular3dgs_b200 as pkg
+    from binocular3dgs_b200 import _backend
+    arm = Arm()
+    arm.name, arm.is_native, arm.null_grads = "native", True, True
+    # the device-timed loop drives the C-ABI through the ctypes host side (per-stage profiling,
+    # the DP gradient sink); the public surface (e2e) runs on the compiled host side when built
+    arm.C = _backend.native()
+    arm.GaussianRasterizer = pkg.GaussianRasterizer
+    arm.GaussianRasterizationSettings = pkg.GaussianRasterizationSettings
+    arm.describe = arm.C.version() + "; public surface on " + getattr(pkg._C, "name", "?")
+    return arm
+
+
+def load_reference():
+    """The stock reference package from baseline/_ref, and nothing of this repository."""
+    pkg_dir = os.path.join(REF_DIR, "diff_gaussian_rasterization")
+    so = [f for f in (os.listdir(pkg_dir) if os.path.isdir(pkg_dir) else []) if f.startswith("_C") and f.endswith(".so")]
+    if not so:
+        return None
+    sys.path.insert(0, REF_DIR)           # ahead of ROOT, whose diff_gaussian_rasterization/ is OUR drop-in
+    import diff_gaussian_rasterization as dgr
+    assert os.path.abspath(dgr.__file__).startswith(REF_DIR + os.sep), dgr.__file__
+    arm = Arm()
+    arm.name = "reference"
+    arm.C = dgr._C
+    arm.GaussianRasterizer = dgr.GaussianRasterizer
+    arm.GaussianRasterizationSettings = dgr.GaussianRasterizationSettings
+    info = {}
+    try:
+        info = json.load(open(os.path.join(REF_DIR, "BUILD_INFO.json")))
+    except Exception:
+        pass
+    arm.describe = "stock diff_gaussian_rasterization (%s), built by its own setup.py, %s" % (
+        info.get("extension", so[0]), info.get("arch", "sm_100a"))
+    return arm
+
+
+def load_veneer():
+    from oracle import refbackend
+    if not refbackend.available():
+        return None
+    from binocular3dgs_b200.rasterizer import GaussianRasterizationSettings, make_surface
+    arm = Arm()
+    arm.name = "veneer"
+    arm.C = refbackend.reference()
+    S = make_surface(arm.C)
+    arm.GaussianRasterizer, arm.GaussianRasterizationSettings = S.GaussianRasterizer, GaussianRasterizationSettings
+    arm.describe = "reference kernels (oracle/_ref/libdgr_ref.so) under this repository's host code"
+    return arm
+
+
+# --------------------------------------------------------------------------- workloads
+class Workload:
+    """One BASELINE.json configuration as seeded synthetic input, resident on `dev`."""
+
+    def __init__(self, name, kind, dev, rank, pair=False):
+        cfg = CONFIGS[name]
+        self.name, self.kind, self.pair, self.dev = name, kind, pair, dev
+        self.W, self.H, self.P = cfg["width"], cfg["height"], cfg["P"]
+        self.scene_c = make_scene(self.P, seed=0, kind=kind)
+        self.scene = self.scene_c.to(dev)
+        self.M = self.scene.shs.shape[1]
+        self.n_views = 8
+        # rank-distinct cameras: a ring of views around the scene; each step cycles through 8.
+        # pair: the second render of a step is the same view shifted along the camera's x axis
+        # (scene/__init__.py:96-115, train.py:122-127), shift drawn once per view from +-U(0.1, 0.4)
+        rs = np.random.RandomState(1234 + rank)
+        self.cams_c, self.cams2_c = [], []
+        for v in range(self.n_views):
+            az, el = 0.3 + 0.785 * ((v + rank * 3) % 8), 0.2 - 0.05 * (v % 3)
+            self.cams_c.append(make_camera(self.W, self.H, cfg["fovx"], azimuth=az, elevation=el))
+            if pair:
+                s = float(rs.uniform(0.1, 0.4)) * (1.0 if rs.rand() < 0.5 else -1.0)
+                self.cams2_c.append(make_camera(self.W, self.H, cfg["fovx"], azimuth=az, elevation=el, shift_x=s))
+        self.cams = [c.to(dev) for c in self.cams_c]
+        self.cams2 = [c.to(dev) for c in self.cams2_c]
+        self.bg = torch.zeros(3, device=dev)
+        self.gc, self.gd, self.ga = (t.to(dev) for t in make_pixel_grads(self.W, self.H, seed=1))
+        self.zero = torch.zeros_like(self.gd)       # the reference's autograd materialises zero grads
+        self.views_per_step = 2 if pair else 1
+
+    def label(self):
+        s = self.scene
+        return "%s%s: %d Gaussians (%s, seed 0, SH degree %d, M=%d), %dx%d, 8 cameras on a ring%s" % (
+            self.name, "_pair" if self.pair else "", self.P, self.kind, s.sh_degree, self.M, self.W, self.H,
+            "; 2 renders per step (view + x-shifted view), depth gradient on the first only" if self.pair else "")
+
+
+def raw_forward(C, wl, cam):
+    s, e = wl.scene, torch.empty(0)
+    return C.rasterize_gaussians(wl.bg, s.means3D, e, s.opacities, s.scales, s.rotations, 1.0, e,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy,
+                                 wl.H, wl.W, s.shs, s.sh_degree, cam.camera_center, False, False)
+
+
+def raw_backward(C, wl, cam, out, gd, ga):
+    s, e = wl.scene, torch.empty(0)
+    R, color, depth, alpha, radii, geom, binning, img = out
+    return C.rasterize_gaussians_backward(wl.bg, s.means3D, radii, e, s.scales, s.rotations, 1.0, e,
+                                          cam.world_view_transform, cam.full_proj_transform, cam.tanfovx,
+                                          cam.tanfovy, wl.gc, gd, ga, s.shs, s.sh_degree, cam.camera_center,
+                                          geom, R, binning, img, alpha, False)
+
+
+def make_step(arm, wl, bucket):
+    """Device-resident step: forward(s) then backward(s) of one view (or binocular pair),
+    then the gradient exchange when running data-parallel."""
+    C = arm.C
+    none_or_zero = None if arm.null_grads else wl.zero
+
+    def step(i):
+        v = i % wl.n_views
+        out = raw_forward(C, wl, wl.cams[v])
+        if wl.pair:
+            out2 = raw_forward(C, wl, wl.cams2[v])
+            raw_backward(C, wl, wl.cams2[v], out2, none_or_zero, none_or_zero)     # colour loss only
+        raw_backward(C, wl, wl.cams[v], out, wl.gd, wl.ga)
+        if bucket is not None:
+            bucket.all_reduce(average=True)
+        return out
+    return step
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="lego", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "veneer"])
+    ap.add_argument("--config", default="dtu", choices=sorted(CONFIGS) + ["fern_pair"])
     ap.add_argument("--kind", default="cube", choices=["cube", "shell"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other configs and the §8(f) rows")
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -142,63 +321,27 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.impl == "reference":
-        from oracle import refbackend
-        if not refbackend.available():
-            if rank == 0:
-                os.write(json_fd, (json.dumps({"impl": "reference", "unavailable":
-                                               "oracle/_ref/libdgr_ref.so was not built"}) + "\n").encode())
-            return
-        back = refbackend.reference()
-    else:
-        from binocular3dgs_b200 import _backend
-        back = _backend.native()
-    # the public surface (e2e) runs on the compiled host side when it has been built; the
-    # device-timed loop below drives the C-ABI through the ctypes host side (per-stage
-    # profiling, the DP gradient sink) — same library, same kernels
-    S = make_surface(_backend.preferred() if args.impl == "native" else back)
+    arm = {"native": load_native, "reference": load_reference, "veneer": load_veneer}[args.impl]()
+    if arm is None:
+        if rank == 0:
+            why = ("baseline/_ref holds no built diff_gaussian_rasterization (run baseline/build_reference.sh)"
+                   if args.impl == "reference" else "oracle/_ref/libdgr_ref.so was not built")
+            os.write(json_fd, (json.dumps({"impl": args.impl, "unavailable": why}) + "\n").encode())
+        return
+    use_dp = world > 1 and arm.is_native
 
-    cfg = CONFIGS[args.config]
-    W, H, P = cfg["width"], cfg["height"], cfg["P"]
-    scene_c = make_scene(P, seed=0, kind=args.kind)
-    scene = scene_c.to(dev)
-    M = scene.shs.shape[1]
-    # rank-distinct cameras: a ring of views around the scene; each step cycles through 8
-    n_views = 8
-    cams_c = [make_camera(W, H, cfg["fovx"], azimuth=0.3 + 0.785 * ((v + rank * 3) % 8), elevation=0.2 - 0.05 * (v % 3))
-              for v in range(n_views)]
-    cams = [c.to(dev) for c in cams_c]
-    bg = torch.zeros(3, device=dev)
-    gc, gd, ga = (t.to(dev) for t in make_pixel_grads(W, H, seed=1))
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    e = torch.empty(0)
-    use_dp = world > 1 and args.impl == "native"
-    # world > 1: the bucket lives in symmetric memory and is reduced by b3gs_peer_allreduce
-    # (B3GS_DP=nccl forces the NCCL all-reduce for A/B timing)
-    bucket, bucket_kind = (make_bucket(P, M, dev, prefer_peer=os.environ.get("B3GS_DP", "peer") != "nccl")
-                           if args.impl == "native" else (None, None))
-    if bucket is not None:
-        back.grad_sink = bucket.views()
-
-    # ---------------- device-resident step (value)
-    def step(i):
-        cam = cams[i % n_views]
-        out = back.rasterize_gaussians(bg, scene.means3D, e, scene.opacities, scene.scales, scene.rotations, 1.0, e,
-                                       cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy,
-                                       H, W, scene.shs, scene.sh_degree, cam.camera_center, False, False)
-        R, color, depth, alpha, radii, geom, binning, img = out
-        back.rasterize_gaussians_backward(bg, scene.means3D, radii, e, scene.scales, scene.rotations, 1.0, e,
-                                          cam.world_view_transform, cam.full_proj_transform, cam.tanfovx,
-                                          cam.tanfovy, gc, gd, ga, scene.shs, scene.sh_degree, cam.camera_center,
-                                          geom, R, binning, img, alpha, False)
-        if use_dp:
-            bucket.all_reduce(average=True)
-        return out
+    def make_dp_bucket(w):
+        if not use_dp:
+            return None, None
+        from binocular3dgs_b200.dp import make_bucket
+        return make_bucket(w.P, w.M, dev, prefer_peer=os.environ.get("B3GS_DP", "peer") != "nccl")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -216,47 +359,63 @@ def main():
             flush.zero_()          # L2 flush, outside the event pair
         barrier()
         wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(per)
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, wall
+        return ms, wall, per
+
+    # ---------------- the headline workload, device-resident (value)
+    pair = args.config == "fern_pair"
+    wl = Workload("fern" if pair else args.config, args.kind, dev, rank, pair=pair)
+    W, H, P, M = wl.W, wl.H, wl.P, wl.M
+    bucket, bucket_kind = make_dp_bucket(wl)
+    C = arm.C
+    if bucket is not None:
+        C.grad_sink = bucket.views()
+    step = make_step(arm, wl, bucket)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = back.launch_count()
-    back.profile_enable(True)
-    back.profile_read()
+    profiled = arm.is_native
+    if profiled:
+        C.profile_enable(True)
     for i in range(args.warmup):
         step(i)
         flush.zero_()
-    back.profile_read()                    # drop warm-up samples
-    launches0 = back.launch_count()
-    total_ms, wall = timed(step, args.steps, 0)
-    prof = back.profile_read()
-    launches = back.launch_count() - launches0
-    back.profile_enable(False)
+    if profiled:
+        C.profile_read()                    # drop warm-up samples
+    launches0 = C.launch_count() if arm.is_native else 0
+    total_ms, wall, per_step = timed(step, args.steps, 0)
+    prof = C.profile_read() if profiled else {}
+    launches = (C.launch_count() - launches0) if arm.is_native else None
+    if profiled:
+        C.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = world * 1000.0 / ms_per_step
+    value = world * wl.views_per_step * 1000.0 / ms_per_step
 
     # ---------------- end to end through the public API with host buffers
     pin = lambda t: t.contiguous().pin_memory()
     host_views = []
     with torch.no_grad():
-        for v in range(n_views):
-            out = back.rasterize_gaussians(bg, scene.means3D, e, scene.opacities, scene.scales, scene.rotations, 1.0,
-                                           e, cams[v].world_view_transform, cams[v].full_proj_transform,
-                                           cams[v].tanfovx, cams[v].tanfovy, H, W, scene.shs, scene.sh_degree,
-                                           cams[v].camera_center, False, False)
-            gt = (out[1] * 0.9 + 0.05).clamp(0, 1).cpu()
-            host_views.append(dict(gt=pin(gt), view=pin(cams_c[v].world_view_transform),
-                                   proj=pin(cams_c[v].full_proj_transform), center=pin(cams_c[v].camera_center)))
-    leaves = [t.detach().clone().requires_grad_(True) for t in scene.tensors()]
-    loss_host = torch.zeros(1).pin_memory()
-    h2d = host_views[0]["gt"].numel() * 4 + (16 + 16 + 3) * 4
+        for v in range(wl.n_views):
+            hv = {}
+            for tag, cam_d, cam_c in (("", wl.cams[v], wl.cams_c[v]),) + (
+                    (("2", wl.cams2[v], wl.cams2_c[v]),) if wl.pair else ()):
+                out = raw_forward(C, wl, cam_d)
+                hv["gt" + tag] = pin((out[1] * 0.9 + 0.05).clamp(0, 1).cpu())
+                hv["view" + tag] = pin(cam_c.world_view_transform)
+                hv["proj" + tag] = pin(cam_c.full_proj_transform)
+                hv["center" + tag] = pin(cam_c.camera_center)
+            host_views.append(hv)
+    if arm.is_native:
+        C.grad_sink = None                          # autograd owns the gradient tensors on this path
+    leaves = [t.detach().clone().requires_grad_(True) for t in wl.scene.tensors()]
+    h2d = sum(t.numel() * t.element_size() for t in host_views[0].values())
     d2h = 4
 
     # Double-buffered inputs: while step i computes, the copy stream uploads step i+1's
@@ -268,15 +427,22 @@ def main():
     loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
     staged = {}
     losses = []
+    Settings, Rasterizer = arm.GaussianRasterizationSettings, arm.GaussianRasterizer
 
     def upload(i):
-        hv = host_views[i % n_views]
+        hv = host_views[i % wl.n_views]
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
-            bufs = {k: hv[k].to(dev, non_blocking=True) for k in ("gt", "view", "proj", "center")}
+            bufs = {k: t.to(dev, non_blocking=True) for k, t in hv.items()}
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         staged[i] = (bufs, ev)
+
+    def render(bufs, tag, cam, m, s, q, o, sh):
+        settings = Settings(H, W, cam.tanfovx, cam.tanfovy, wl.bg, 1.0, bufs["view" + tag], bufs["proj" + tag],
+                            wl.scene.sh_degree, bufs["center" + tag], False, False)
+        means2D = torch.zeros_like(m, requires_grad=True)
+        return Rasterizer(settings)(means3D=m, means2D=means2D, opacities=o, shs=sh, scales=s, rotations=q)
 
     def e2e_step(i):
         main = torch.cuda.current_stream(dev)
@@ -287,14 +453,13 @@ def main():
         for t in bufs.values():
             t.record_stream(main)
         upload(i + 1)                  # runs concurrently with this step's kernels
-        cam = cams_c[i % n_views]
+        v = i % wl.n_views
         m, s, q, o, sh = leaves
-        settings = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, bufs["view"], bufs["proj"],
-                                                 scene.sh_degree, bufs["center"], False, False)
-        means2D = torch.zeros_like(m, requires_grad=True)
-        color, radii, depth, alpha = S.GaussianRasterizer(settings)(
-            means3D=m, means2D=means2D, opacities=o, shs=sh, scales=s, rotations=q)
+        color, radii, depth, alpha = render(bufs, "", wl.cams_c[v], m, s, q, o, sh)
         loss = (color - bufs["gt"]).abs().mean() + 1e-3 * depth.mean() + 1e-3 * alpha.mean()
+        if wl.pair:
+            color2 = render(bufs, "2", wl.cams2_c[v], m, s, q, o, sh)[0]
+            loss = loss + (color2 - bufs["gt2"]).abs().mean()
         for t in leaves:
             t.grad = None
         loss.backward()
@@ -308,7 +473,6 @@ def main():
         main.wait_event(staged[i + 1][1])            # next step's upload completes inside this step
         return None
 
-    back.grad_sink = None                          # autograd owns the gradient tensors on this path
     e2e_steps = max(10, args.steps)
     e2e_warm = max(3, args.warmup)
     for i in range(e2e_warm):
@@ -316,63 +480,81 @@ def main():
         flush.zero_()
     staged.clear()
     torch.cuda.synchronize()
-    e2e_ms, _ = timed(lambda i: e2e_step(i + e2e_warm), e2e_steps, 0)
+    e2e_ms, _, _ = timed(lambda i: e2e_step(i + e2e_warm), e2e_steps, 0)
+    staged.clear()
     assert all(np.isfinite(losses)), "non-finite loss in the e2e loop"
-    e2e_value = world * 1000.0 * e2e_steps / e2e_ms
+    e2e_value = world * wl.views_per_step * 1000.0 * e2e_steps / e2e_ms
 
     # ---------------- roofline of the dominant kernel
     roofline, kernels = None, {}
     peak, peak_src = measured_peaks()
-    if args.impl == "native" and prof:
+    if arm.is_native and prof:
+        if bucket is not None:
+            C.grad_sink = bucket.views()
         out = step(0)
         torch.cuda.synchronize()
-        R = out[0]
-        n_contrib = back.blob_view(out[7], "image", "n_contrib", torch.int32, W * H, W, H)
+        R = int(out[0])
+        n_contrib = C.blob_view(out[7], "image", "n_contrib", torch.int32, W * H, W, H)
         I_f = tile_work(n_contrib, W, H)
         T, N = ((W + 15) // 16) * ((H + 15) // 16), W * H
-        D = scene.sh_degree
-        alg = {  # algorithmic bytes per launch, SURVEY.md §8(d)
-            "preprocess": P * (44 + 12 * (D + 1) ** 2) + 75 * P,
-            # 4 passes x (4 B hist read + 8 B read + 8 B write) + gather-scan of tiles_touched
-            "depth_sort": P * (4 * 20 + 16),
-            # emit (tile,id) 8 B + passes x 20 B + 4 B boundary scan per instance, 8 B per tile
-            "binning": 28 * P + R * (8 + 20 * (1 if T <= 256 else 2 if T <= 65536 else 3) + 4) + 8 * T,
-            "composite_forward": 44 * I_f + 8 * T + 24 * N,
-            "grad_zero": 48 * P,
-            "composite_backward": 44 * I_f + 8 * T + 28 * N + 80 * I_f,
-            "preprocess_backward": P * (111 + 12 * (D + 1) ** 2) + P * (40 + 12 * (D + 1) ** 2),
-        }
+        alg = algorithmic_bytes(P=P, R=R, T=T, N=N, D=wl.scene.sh_degree, I_f=I_f)
         for k, (ms, calls) in prof.items():
-            if calls:
+            if calls and k in alg:
                 dur = ms / calls
                 kernels[k] = {"ms": round(dur, 4), "share": round(ms / total_ms, 4),
-                              "alg_bytes": int(alg[k]), "GBps": round(alg[k] / dur / 1e6, 1)}
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+                              "calls_per_step": calls / args.steps, "alg_bytes": int(alg[k]),
+                              "GBps": round(alg[k] / dur / 1e6, 1)}
+        dom = max(kernels, key=lambda k: kernels[k]["share"])
         achieved = kernels[dom]["GBps"]
-        try:  # dram bytes per launch from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        try:  # dram bytes per launch from the committed ncu --set full capture of this workload
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name, {}).get(dom)
         except Exception:
             traffic = None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "I_f": I_f, "R": R,
-                    "note": "composite kernels are FP32-issue bound, not HBM bound (ncu: issue slots ~83% busy, "
-                            "DRAM <1%); see DESIGN.md"}
+                    "note": "the composite kernels are FP32-issue bound, not HBM bound (ncu: issue slots ~80% busy, "
+                            "DRAM ~1%); the HBM-bound kernels are listed with their own GB/s under `kernels`; "
+                            "see DESIGN.md §5"}
+
+    # ---------------- the other BASELINE.json configurations, device-resident, brief
+    configs = None
+    if not args.no_extra:
+        configs = {}
+        for cname, cpair in (("lego", False), ("fern", True)):
+            if cname == wl.name and cpair == wl.pair:
+                continue
+            key = cname + ("_pair" if cpair else "")
+            try:
+                w2 = Workload(cname, args.kind, dev, rank, pair=cpair)
+                b2, _ = make_dp_bucket(w2)
+                if arm.is_native:
+                    C.grad_sink = b2.views() if b2 is not None else None
+                st2 = make_step(arm, w2, b2)
+                n2 = max(20, min(args.steps, 50))
+                ms2, _, _ = timed(st2, n2, 5)
+                configs[key] = {"workload": w2.label(), "ms_per_step": round(ms2 / n2, 4), "steps": n2,
+                                "value": round(world * w2.views_per_step * 1000.0 * n2 / ms2, 2), "unit": UNIT}
+                del w2, b2, st2
+            except Exception as ex:      # never let a secondary row break the headline line
+                configs[key] = {"error": repr(ex)}
+        if arm.is_native:
+            C.grad_sink = None
 
     # ---------------- CPU baseline (oracle port), rank 0 only, bounded sample
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # N=1 only (torchrun pins OMP threads to 1)
+    if rank == 0 and world == 1 and arm.is_native and not args.no_cpu_baseline:   # N=1 only (torchrun pins OMP threads to 1)
         from oracle import cpu_oracle as orc
-        a = [t.numpy() for t in scene_c.tensors()]
-        gcn, gdn, gan = (t.cpu().numpy() for t in (gc, gd, ga))
+        a = [t.numpy() for t in wl.scene_c.tensors()]
+        gcn, gdn, gan = (t.cpu().numpy() for t in (wl.gc, wl.gd, wl.ga))
         views, t0 = 0, time.perf_counter()
         while True:
-            cam = cams_c[views % n_views]
+            cam = wl.cams_c[views % wl.n_views]
             cam_args = (cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), cam.camera_center.numpy())
             of = orc.rasterize_forward(a[0], a[1], a[2], a[3], a[4], *cam_args, np.zeros(3, np.float32), W, H,
-                                       cam.tanfovx, cam.tanfovy, scene_c.sh_degree)
+                                       cam.tanfovx, cam.tanfovy, wl.scene_c.sh_degree)
             orc.rasterize_backward(of, a[0], a[1], a[2], a[4], *cam_args, np.zeros(3, np.float32), W, H, cam.tanfovx,
-                                   cam.tanfovy, scene_c.sh_degree, gcn, gdn, gan)
+                                   cam.tanfovy, wl.scene_c.sh_degree, gcn, gdn, gan)
             views += 1
             el = time.perf_counter() - t0
             if el >= args.cpu_sample_seconds or views >= 64:
@@ -380,58 +562,42 @@ def main():
         cpu_baseline = {"value": round(views / el, 4), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                         "sample": "%d views (fwd+bwd) of the same workload in %.1f s, OpenMP over tiles" % (views, el)}
 
-    # ---------------- §8(f) rank 1: fused photometric loss, timed beside the torch-style one
+    # ---------------- §8(f) rows next to the rasterizer
     next_rows = None
-    if rank == 0 and world == 1 and args.impl == "native":
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_loss
-            next_rows = {"photometric_loss": bench_loss.measure(dev, 3, H, W)}
-        except Exception as ex:  # never let the auxiliary row break the headline line
-            next_rows = {"photometric_loss": {"error": repr(ex)}}
-        try:  # §8(f) rank 2 at the size of the config that uses it (LLFF fern, 1008x756)
-            next_rows["binocular_loss"] = bench_loss.measure_binocular(dev)
-        except Exception as ex:
-            next_rows["binocular_loss"] = {"error": repr(ex)}
-        try:  # §8(f) rank 3 at the bench's own P and M
-            import bench_params
-            next_rows["parameter_plumbing"] = bench_params.measure(dev, P, M)
-        except Exception as ex:
-            next_rows["parameter_plumbing"] = {"error": repr(ex)}
-        # The native arm never executes anything under oracle/: the reference's own kernels
-        # for these two rows are timed by `bench.py --impl reference` (same keys, below).
-        try:  # §8(f) rank 4 on an SfM-like cloud
-            import bench_knn
-            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3, which="native")
-        except Exception as ex:
-            next_rows["dist_cuda2"] = {"error": repr(ex)}
-        try:  # everything together: the reference's training iteration on the binocular config
-            import bench_iteration
-            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5, which=("native",))
-        except Exception as ex:
-            next_rows["train_iteration"] = {"error": repr(ex)}
-    elif rank == 0 and world == 1 and args.impl == "reference":
+    if rank == 0 and world == 1 and not args.no_extra and args.impl in ("native", "veneer"):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         next_rows = {}
-        try:  # the reference's simple-knn kernel (oracle/_ref/libknn_ref.so) on the same cloud
-            import bench_knn
-            next_rows["dist_cuda2"] = bench_knn.measure(1_000_000, "clustered", 3, which="reference")
-        except Exception as ex:
-            next_rows["dist_cuda2"] = {"error": repr(ex)}
-        try:  # the reference's kernels + everything around them as the reference writes it
-            import bench_iteration
-            next_rows["train_iteration"] = bench_iteration.measure(dev, "fern", 20, 5, which=("reference_style",))
-        except Exception as ex:
-            next_rows["train_iteration"] = {"error": repr(ex)}
+
+        def row(name, fn):
+            try:
+                next_rows[name] = fn()
+            except Exception as ex:
+                next_rows[name] = {"error": repr(ex)}
+        if arm.is_native:
+            # The native arm never executes anything under oracle/: the reference's kernels for
+            # dist_cuda2 / train_iteration are timed by `--impl veneer` (same keys).
+            row("photometric_loss", lambda: __import__("bench_loss").measure(dev, 3, 800, 800))
+            row("binocular_loss", lambda: __import__("bench_loss").measure_binocular(dev))
+            row("parameter_plumbing", lambda: __import__("bench_params").measure(dev, 200_000, 4))
+            row("dist_cuda2", lambda: __import__("bench_knn").measure(1_000_000, "clustered", 3, which="native"))
+            row("train_iteration", lambda: __import__("bench_iteration").measure(dev, "fern", 20, 5, which=("native",)))
+        else:
+            row("dist_cuda2", lambda: __import__("bench_knn").measure(1_000_000, "clustered", 3, which="reference"))
+            row("train_iteration",
+                lambda: __import__("bench_iteration").measure(dev, "fern", 20, 5, which=("reference_style",)))
 
     if rank == 0:
+        repo_libs = mapped_repo_libraries()
+        if args.impl == "reference":
+            assert "binocular3dgs_b200" not in sys.modules, "the reference arm must not import the product"
+            assert not [l for l in repo_libs if not l.startswith("baseline" + os.sep)], repo_libs
+        per_sorted = sorted(per_step)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %d Gaussians (%s, seed 0, SH degree %d, M=%d), %dx%d, 8 cameras on a ring"
-                                   % (args.config, P, args.kind, scene.sh_degree, M, W, H),
-                       "P": P, "width": W, "height": H,
+            "config": {"workload": wl.label(), "P": P, "width": W, "height": H,
+                       "views_per_step": wl.views_per_step,
                        "parallelism": ("view-parallel dp%d, %s of the %d-byte/Gaussian gradient bucket"
                                        % (world, "in-place two-shot all-reduce over NVLink peer memory "
                                           "(b3gs_peer_allreduce)" if bucket_kind == "peer" else "NCCL all-reduce",
@@ -443,19 +609,26 @@ def main():
                     "what": "GaussianRasterizer forward + L1 loss + autograd backward; every step uploads one view's "
                             "camera + GT image from pinned host memory (double-buffered on a copy stream, completed "
                             "inside the step's event pair) and copies the loss back to pinned host memory"},
-            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": round(wall, 4),
-            "impl": args.impl, "library": back.version(),
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": round(wall, 4),
+            "step_ms": {"min": round(per_sorted[0], 4), "median": round(per_sorted[len(per_sorted) // 2], 4),
+                        "max": round(per_sorted[-1], 4)},
+            "impl": args.impl, "library": arm.describe, "repo_libraries_mapped": repo_libs,
         }
         if roofline:
             line["roofline"] = roofline
             line["kernels"] = kernels
+        if configs:
+            line["configs"] = configs
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if next_rows:
             line["next_rows"] = next_rows
         if args.impl == "reference":
-            line["reference_kind"] = ("reference CUDA kernels (oracle/_ref, unmodified sources) on the same GPU; the "
-                                      "reference has no CPU implementation of this path")
+            line["reference_kind"] = ("UNMODIFIED reference: baseline/_ref/diff_gaussian_rasterization (stock setup.py "
+                                      "build) through its own GaussianRasterizer / _C on the same GPU; the reference "
+                                      "has no CPU implementation of this path")
+        elif args.impl == "veneer":
+            line["reference_kind"] = arm.describe
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

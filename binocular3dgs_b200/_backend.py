@@ -95,6 +95,11 @@ class Backend:
         self._backward = g("backward")
         self._backward.argtypes = _BWD_ARGTYPES
         self._backward.restype = ctypes.c_int
+        # b3gs_backward_flags (B3GS_BWD_ACCUMULATE): ours only
+        self._backward_flags = getattr(self.lib, prefix + "backward_flags", None)
+        if self._backward_flags is not None:
+            self._backward_flags.argtypes = [ctypes.c_uint] + _BWD_ARGTYPES
+            self._backward_flags.restype = ctypes.c_int
         self._mark_visible = g("mark_visible")
         self._mark_visible.argtypes = [ctypes.c_int, _F, _F, _F, _F, ctypes.c_void_p]
         self._mark_visible.restype = ctypes.c_int
@@ -120,10 +125,17 @@ class Backend:
             g("profile_stage_name").restype = ctypes.c_char_p
             g("profile_stage_name").argtypes = [ctypes.c_int]
             g("profile_read").argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-        # Optional dict name -> preallocated tensor ("means3D", "shs", "opacities", "scales",
-        # "rotations") the backward writes its parameter gradients INTO instead of
+        # Optional gradient sink: the backward writes its five parameter gradients ("means3D",
+        # "shs", "opacities", "scales", "rotations") INTO preallocated memory instead of
         # allocating them — how dp.GradientBucket receives gradients without a pack copy.
+        # Either a dict name -> tensor (every backward overwrites it; for callers that drive
+        # `_C` directly, one backward per step) or an object with
+        # ``acquire(autograd: bool) -> (dict | None, accumulate: bool)`` (dp.GradientBucket):
+        # the first backward of a step gets the views; later ones get fresh tensors under
+        # autograd (which adds them into the stolen views itself) or accumulate in the kernel
+        # (B3GS_BWD_ACCUMULATE) when `_C` is driven directly.
         self.grad_sink = None
+        self.in_autograd = False     # set by rasterizer._RasterizeGaussians.backward around its call
         # our C-ABI treats NULL dL/ddepth, dL/dalpha as zeros; the reference veneer does not
         self.accepts_null_grads = prefix == "b3gs_"
         # One persistent C callback; `user` is the slot index (0 geom, 1 binning, 2 image).
@@ -247,7 +259,11 @@ class Backend:
             dL_dsh = alloc((P, M, 3), **o)
             dL_dscales = alloc((P, 3), **o)
             dL_drotations = alloc((P, 4), **o)
-            sink = self.grad_sink
+            sink, accumulate = self.grad_sink, False
+            if sink is not None and hasattr(sink, "acquire"):
+                sink, accumulate = sink.acquire(self.in_autograd)
+            if accumulate and self._backward_flags is None:
+                raise RuntimeError(f"{self.name}: this library cannot accumulate into a gradient sink")
             if sink is not None and P != 0:
                 def take(name, t):
                     v = sink.get(name)
@@ -272,7 +288,8 @@ class Backend:
                 )
                 rad = radii.contiguous()
                 stream = torch.cuda.current_stream(dev).cuda_stream
-                rc = self._backward(
+                fn = self._backward if not accumulate else (lambda *a: self._backward_flags(1, *a))
+                rc = fn(
                     P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(alp), _ptr(sca),
                     float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
                     float(tan_fovy), _ptr(rad), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
@@ -330,7 +347,25 @@ class CompiledBackend:
             return self._ct.rasterize_gaussians_backward(*args)
         return self._m.rasterize_gaussians_backward(*args)
 
-    def __getattr__(self, name):                # lib, launch_count, profile_*, blob_view, grad_sink, ...
+    # state that lives on the ctypes backend must be SET there too (a plain attribute
+    # assignment would land on this wrapper and be ignored by the backward)
+    @property
+    def grad_sink(self):
+        return self._ct.grad_sink
+
+    @grad_sink.setter
+    def grad_sink(self, value):
+        self._ct.grad_sink = value
+
+    @property
+    def in_autograd(self):
+        return self._ct.in_autograd
+
+    @in_autograd.setter
+    def in_autograd(self, value):
+        self._ct.in_autograd = value
+
+    def __getattr__(self, name):                # lib, launch_count, profile_*, blob_view, ...
         return getattr(self._ct, name)
 
 

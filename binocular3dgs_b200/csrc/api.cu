@@ -82,22 +82,28 @@ static char* align_ptr(void* p) {
     return reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(p), 256));
 }
 
-// One event per host thread: "R has landed in the pinned word".
-static cudaEvent_t count_event() {
-    static thread_local cudaEvent_t ev = nullptr;
-    if (!ev) {
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
-    }
-    return ev;
+// One event and one pinned word per (host thread, device): "R has landed in the pinned word".
+// Events belong to the device that was current when they were created, so a thread that
+// renders on several GPUs needs one per device.
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices ? dev : -1;
 }
-
-// One pinned word per host thread for the R read-back.
+static cudaEvent_t count_event() {
+    static thread_local cudaEvent_t ev[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) ev[dev] = nullptr;
+    return ev[dev];
+}
 static int* pinned_word() {
-    static thread_local int* w = nullptr;
-    if (!w) {
-        if (cudaHostAlloc(reinterpret_cast<void**>(&w), sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) w = nullptr;
-    }
-    return w;
+    static thread_local int* w[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
+    if (!w[dev] && cudaHostAlloc(reinterpret_cast<void**>(&w[dev]), sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess)
+        w[dev] = nullptr;
+    return w[dev];
 }
 
 // ---- optional per-stage device timing (bench.py roofline) ---------------------
@@ -301,7 +307,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
     return B3GS_OK;
 }
 
-int b3gs_backward(int P, int D, int M, int R, const float* background, int width, int height,
+int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float* background, int width, int height,
                   const float* means3D, const float* shs, const float* colors_precomp, const float* alphas,
                   const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
                   const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
@@ -370,12 +376,28 @@ int b3gs_backward(int P, int D, int M, int R, const float* background, int width
     pa.dL_dmean2D = dL_dmean2D; pa.dL_dconic = dL_dconic; pa.dL_dopacity = dL_dopacity; pa.dL_dcolor = dL_dcolor;
     pa.dL_ddepth = dL_ddepth; pa.dL_dmean3D = dL_dmean3D; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
     pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
+    pa.accumulate = (flags & B3GS_BWD_ACCUMULATE) ? 1 : 0;
     {
         StageTimer t_(ST_PREPROCESS_BWD, st);
         launch_preprocess_backward(pa, st);
     }
     B3_CHECK_STAGE("preprocess_backward");
     return B3GS_OK;
+}
+
+int b3gs_backward(int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
+                  const float* shs, const float* colors_precomp, const float* alphas, const float* scales,
+                  float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                  const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                  char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                  const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D, float* dL_dconic,
+                  float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+                  float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream) {
+    return b3gs_backward_flags(0u, P, D, M, R, background, width, height, means3D, shs, colors_precomp, alphas, scales,
+                               scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
+                               tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpix_depth,
+                               dL_dalphas, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
+                               dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream);
 }
 
 int b3gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/,

@@ -131,6 +131,7 @@ struct PreBackwardArgs {
     float* dL_dsh;       // [P,M,3] or nullptr
     float* dL_dscale;    // [P,3]
     float* dL_drot;      // [P,4]
+    int accumulate;      // != 0: dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale, dL_drot are added to, not overwritten
 };
 void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream);
 

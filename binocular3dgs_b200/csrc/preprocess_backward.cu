@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
     for (int k = 0; k < B3_GRAD_STRIDE; k++) g[k] = 0.f;
 
     const bool visible = p.radii[idx] > 0;
+    const bool acc = p.accumulate != 0;
     const int ncoef = (p.D + 1) * (p.D + 1);
     float* dsh = p.dL_dsh ? p.dL_dsh + i * p.M * 3 : nullptr;
 
@@ -198,9 +199,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
 #define DSH(k, coef)                                             \
     {                                                            \
         const float cf_ = (coef);                                \
-        dsh[3 * (k) + 0] = cf_ * dRGB[0];                        \
-        dsh[3 * (k) + 1] = cf_ * dRGB[1];                        \
-        dsh[3 * (k) + 2] = cf_ * dRGB[2];                        \
+        if (acc) {                                               \
+            dsh[3 * (k) + 0] += cf_ * dRGB[0];                   \
+            dsh[3 * (k) + 1] += cf_ * dRGB[1];                   \
+            dsh[3 * (k) + 2] += cf_ * dRGB[2];                   \
+        } else {                                                 \
+            dsh[3 * (k) + 0] = cf_ * dRGB[0];                    \
+            dsh[3 * (k) + 1] = cf_ * dRGB[1];                    \
+            dsh[3 * (k) + 2] = cf_ * dRGB[2];                    \
+        }                                                        \
     }
             const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
             const float C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
             }
 #undef SHV
 #undef DSH
-            for (int k = ncoef; k < p.M; k++) {
+            for (int k = ncoef; k < p.M && !acc; k++) {
                 dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f;
             }
             const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
             // dL/dscale as written is w.r.t. the UNSCALED parameter only through s; it
             // stores dot(Rt, dMt) without the modifier (backward.cu:322-325) — kept.
         }
-    } else if (dsh) {
+    } else if (dsh && !acc) {
         for (int k = 0; k < p.M * 3; k++) dsh[k] = 0.f;
     }
 
@@ -317,20 +324,36 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
     p.dL_dmean2D[3 * i + 1] = g[B3_G_MEAN2D_Y];
     p.dL_dmean2D[3 * i + 2] = 0.f;
     reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(g[B3_G_CONIC_X], g[B3_G_CONIC_Y], 0.f, g[B3_G_CONIC_W]);
-    p.dL_dopacity[idx] = g[B3_G_OPACITY];
     p.dL_dcolor[3 * i] = g[B3_G_COLOR_R];
     p.dL_dcolor[3 * i + 1] = g[B3_G_COLOR_G];
     p.dL_dcolor[3 * i + 2] = g[B3_G_COLOR_B];
     p.dL_ddepth[idx] = g[B3_G_DEPTH];
-    p.dL_dmean3D[3 * i] = dmean[0];
-    p.dL_dmean3D[3 * i + 1] = dmean[1];
-    p.dL_dmean3D[3 * i + 2] = dmean[2];
 #pragma unroll
     for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
-    p.dL_dscale[3 * i] = dscale[0];
-    p.dL_dscale[3 * i + 1] = dscale[1];
-    p.dL_dscale[3 * i + 2] = dscale[2];
-    reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
+    // The five parameter gradients: overwritten, or — B3GS_BWD_ACCUMULATE, the second view of a
+    // step writing into the same exchange bucket — added to what the earlier view left there
+    // (dL_dsh was accumulated where it was formed, above).
+    if (acc) {
+        p.dL_dopacity[idx] += g[B3_G_OPACITY];
+        p.dL_dmean3D[3 * i] += dmean[0];
+        p.dL_dmean3D[3 * i + 1] += dmean[1];
+        p.dL_dmean3D[3 * i + 2] += dmean[2];
+        p.dL_dscale[3 * i] += dscale[0];
+        p.dL_dscale[3 * i + 1] += dscale[1];
+        p.dL_dscale[3 * i + 2] += dscale[2];
+        float4* r4 = reinterpret_cast<float4*>(p.dL_drot) + idx;
+        const float4 o = *r4;
+        *r4 = make_float4(o.x + drot.x, o.y + drot.y, o.z + drot.z, o.w + drot.w);
+    } else {
+        p.dL_dopacity[idx] = g[B3_G_OPACITY];
+        p.dL_dmean3D[3 * i] = dmean[0];
+        p.dL_dmean3D[3 * i + 1] = dmean[1];
+        p.dL_dmean3D[3 * i + 2] = dmean[2];
+        p.dL_dscale[3 * i] = dscale[0];
+        p.dL_dscale[3 * i + 1] = dscale[1];
+        p.dL_dscale[3 * i + 2] = dscale[2];
+        reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
+    }
 }
 
 void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream) {

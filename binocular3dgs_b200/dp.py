@@ -9,9 +9,24 @@ summed with ONE in-place all-reduce over a flat FP32 bucket.
 ``GradientBucket`` is that bucket.  Its segments are laid out
 ``[means3D 3 | sh 3M | opacity 1 | scales 3 | rotations 4]`` × P as five contiguous
 arrays, and the tensors handed out by :meth:`views` alias it, so when the backward of
-the operator writes its outputs *into* those views (``Backend.grad_sink``) there is no
-pack/copy step between the backward kernel and NCCL: the kernel's stores are the
-collective's send buffer.
+the operator writes its outputs *into* those views (``_C.grad_sink = bucket``) there is no
+pack/copy step between the backward kernel and the collective: the kernel's stores are
+the collective's send buffer.
+
+Which bucket for which trainer
+* The tensors fed to the rasterizer are LEAVES (activated parameters held directly, or
+  ``_C`` driven without autograd): ``_C.grad_sink = bucket``.  The first backward of a step
+  writes into the bucket and autograd adopts those views as ``.grad`` without a copy; a
+  second backward in the same step (the binocular pair, train.py:100,128) is added by
+  autograd in place — or, without autograd, accumulated by the kernel itself
+  (``B3GS_BWD_ACCUMULATE``).  ``bucket.all_reduce()`` ends the step.
+* The rasterizer inputs are COMPUTED from raw parameters (the reference's GaussianModel:
+  ``exp`` / ``sigmoid`` / ``normalize`` / ``cat``, scene/gaussian_model.py:95-115): what must be
+  summed over ranks is the gradient of the RAW parameters, which autograd forms after the
+  rasterizer's backward.  Use :class:`ParameterBucket`: it points every parameter's
+  ``.grad`` at a slice of one flat buffer before ``loss.backward()``, autograd accumulates
+  there in place, and one all-reduce of the flat buffer follows.  A grad sink must NOT be
+  used for this case: it would reduce gradients the optimizer never reads.
 """
 from __future__ import annotations
 
@@ -46,6 +61,22 @@ class GradientBucket:
         """Tensors aliasing the bucket, one per parameter group."""
         return self._views
 
+    # ---- gradient-sink protocol (``_C.grad_sink = bucket``; _backend.Backend.rasterize_gaussians_backward)
+    _fresh = True
+
+    def begin_step(self):
+        """The next backward overwrites the bucket (called by :meth:`all_reduce`)."""
+        self._fresh = True
+
+    def acquire(self, autograd: bool):
+        """-> (views or None, accumulate).  First backward of a step: the views, overwritten.
+        Later ones: None under autograd (fresh tensors; autograd adds them into the adopted
+        views), else the views again with kernel-side accumulation."""
+        if self._fresh:
+            self._fresh = False
+            return self._views, False
+        return (None, False) if autograd else (self._views, True)
+
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
@@ -58,11 +89,16 @@ class GradientBucket:
                 self._views[name].copy_(g.reshape(self._views[name].shape))
 
     def all_reduce(self, group=None, average: bool = True, async_op: bool = False):
-        """Sum (or average) the bucket over the ranks of ``group``; in place."""
+        """Sum (or average) the bucket over the ranks of ``group``; in place.  Ends the step
+        for the gradient-sink protocol."""
+        self.begin_step()
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
+        if average and async_op:
+            raise ValueError("average=True needs the result: use async_op=False, or average=False and scale "
+                             "after work.wait()")
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        if average and not async_op:
+        if average:
             self.flat.mul_(1.0 / dist.get_world_size(group))
         return work
 
@@ -80,15 +116,25 @@ class PeerGradientBucket(GradientBucket):
     """
 
     def __init__(self, P: int, M: int, device, group=None, dtype=torch.float32):
-        import ctypes
-
-        import torch.distributed._symmetric_memory as symm_mem
-        from . import _backend
         if dtype != torch.float32:
             raise RuntimeError("PeerGradientBucket is float32 only")
         super().__init__(P, M, "meta")              # sizes and offsets only
+        self._setup_symmetric((self.flat.numel() + 3) // 4 * 4, device, group)
+        off = 0
+        for name in SEGMENTS:
+            cnt = self.P * self.widths[name]
+            shape = (self.P, self.M, 3) if name == "shs" else (self.P, self.widths[name])
+            self._views[name] = self.flat[off:off + cnt].view(shape)
+            off += (cnt + 3) // 4 * 4
+
+    def _setup_symmetric(self, n: int, device, group):
+        import ctypes
+        import os
+
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _backend
         group = dist.group.WORLD if group is None else group
-        n = (self.flat.numel() + 3) // 4 * 4
+        self._group = group
         self.flat = symm_mem.empty(n, dtype=torch.float32, device=device)
         self.flat.zero_()
         self._handle = symm_mem.rendezvous(self.flat, group)
@@ -102,7 +148,6 @@ class PeerGradientBucket(GradientBucket):
         self._fn.restype = ctypes.c_int
         # NVLS: reduce inside the NVSwitch when the buffer has a multicast mapping
         # (B3GS_DP_MULTIMEM=0 keeps the plain peer loads/stores)
-        import os
         self._mc_ptr = 0
         # measured on 8x B200 (18.4 MB bucket): multimem 70 us, plain peer 74 us, NCCL 108 us; on
         # 2x B200: multimem 66 us, plain 46 us, NCCL 64 us -> the switch reduction from 4 ranks up
@@ -116,16 +161,13 @@ class PeerGradientBucket(GradientBucket):
         self._fn_mc.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float,
                                 ctypes.c_void_p]
         self._fn_mc.restype = ctypes.c_int
-        off = 0
-        for name in SEGMENTS:
-            cnt = self.P * self.widths[name]
-            shape = (self.P, self.M, 3) if name == "shs" else (self.P, self.widths[name])
-            self._views[name] = self.flat[off:off + cnt].view(shape)
-            off += (cnt + 3) // 4 * 4
 
     def all_reduce(self, group=None, average: bool = True, async_op: bool = False):
         if async_op:
             raise NotImplementedError("the peer all-reduce is stream-ordered; async_op has no meaning here")
+        if group is not None and group is not self._group:
+            raise ValueError("PeerGradientBucket reduces over the group it was constructed with")
+        self.begin_step()
         if self.world == 1:
             return None
         dev = self.flat.device
@@ -156,6 +198,75 @@ def make_bucket(P: int, M: int, device, group=None, prefer_peer: bool = True):
     return GradientBucket(P, M, device), "nccl"
 
 
+class ParameterBucket:
+    """One flat buffer holding ``.grad`` of every parameter of a model, reduced in one call.
+
+    For trainers whose rasterizer inputs are computed from raw parameters (the reference's
+    ``GaussianModel``).  Per step::
+
+        bucket.attach()            # zero the buffer, point every p.grad at its slice
+        loss.backward()            # autograd accumulates into the slices in place
+        bucket.all_reduce()        # one collective over (11 + 3M) floats per Gaussian
+        optimizer.step(); optimizer.zero_grad(set_to_none=True)     # as train.py:192-193
+
+    ``attach`` must be called again after every ``zero_grad(set_to_none=True)`` and after the
+    densifier replaced the parameters (``rebuild``: scene/gaussian_model.py:334-345 creates new
+    ``nn.Parameter`` objects of a new length).  With ``peer=True`` (CUDA, several ranks) the
+    buffer lives in symmetric memory and is reduced by ``b3gs_peer_allreduce``; otherwise by
+    ``torch.distributed.all_reduce`` (NCCL or gloo).
+    """
+
+    def __init__(self, params, group=None, peer: bool = False):
+        self.group, self.peer = group, peer
+        self.rebuild(params)
+
+    def rebuild(self, params):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("ParameterBucket needs at least one parameter")
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dtype for p in self.params):
+            raise ValueError("all parameters of a ParameterBucket must share device and dtype")
+        self.offsets, off = [], 0
+        for p in self.params:                     # 16-byte aligned slices
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self._inner = None
+        if self.peer and dev.type == "cuda" and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self._inner = _PeerFlat(off, dev, self.group)
+            self.flat = self._inner.flat
+        else:
+            self.flat = torch.zeros(off, dtype=dtype, device=dev)
+        self.slices = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
+
+    def attach(self):
+        self.flat.zero_()
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)    # a fresh view: autograd adds into it in place
+
+    def all_reduce(self, average: bool = True):
+        for p, sl in zip(self.params, self.slices):
+            if p.grad is None or p.grad.data_ptr() != sl.data_ptr():
+                raise RuntimeError("ParameterBucket.all_reduce: a parameter's .grad no longer aliases the bucket "
+                                   "(call attach() before backward, after every zero_grad(set_to_none=True))")
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        if self._inner is not None:
+            self._inner.all_reduce(average)
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if average:
+            self.flat.mul_(1.0 / dist.get_world_size(self.group))
+
+
+class _PeerFlat(PeerGradientBucket):
+    """A bare symmetric-memory float buffer reduced by b3gs_peer_allreduce (no segments)."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        GradientBucket.__init__(self, 0, 0, "meta")
+        self._setup_symmetric((int(n_floats) + 3) // 4 * 4, device, group)
+
+
 def shard_views(num_views: int, rank: int, world_size: int):
     """Indices of the views rank ``rank`` renders this step: view v goes to rank v % N."""
     return list(range(rank, num_views, world_size))
@@ -173,3 +284,40 @@ def reduce_densify_stats(grad_norm: torch.Tensor, visible: torch.Tensor, max_rad
     r = max_radii.clone()
     dist.all_reduce(r, op=dist.ReduceOp.MAX, group=group)
     return packed[0].reshape(grad_norm.shape), packed[1].reshape(visible.shape), r
+
+
+def seed_lockstep(seed: int, rank: Optional[int] = None):
+    """Generator discipline for view-parallel training through densification.
+    ``densify_and_split`` draws the new positions with ``torch.normal`` on CUDA tensors
+    (scene/gaussian_model.py:363-364), i.e. from the CUDA default generator: it must produce
+    the SAME stream on every rank, or the replicas diverge at the first split.  View and
+    binocular-shift sampling use Python ``random`` and the CPU torch generator
+    (train.py:92,125-126): they must DIFFER per rank, or all ranks render the same view."""
+    import random
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)                 # identical on every rank
+    random.seed(seed + 1000003 * (rank + 1))             # rank-distinct
+    torch.default_generator.manual_seed(seed + 1000003 * (rank + 1))
+
+
+def replica_checksum(tensors) -> torch.Tensor:
+    """Order-independent-of-nothing, bit-exact digest of a list of tensors: int64 sums of their
+    raw 32-bit words and of word * (index + 1).  Equal tensors <=> (overwhelmingly) equal digests."""
+    acc = []
+    for t in tensors:
+        w = t.detach().contiguous().view(-1).view(torch.int32).to(torch.int64)
+        idx = torch.arange(1, w.numel() + 1, device=w.device, dtype=torch.int64)
+        acc += [w.sum(), (w * (idx % 65521)).sum(), torch.tensor(w.numel(), device=w.device, dtype=torch.int64)]
+    return torch.stack(acc)
+
+
+def replicas_identical(tensors, group=None) -> bool:
+    """True iff every rank of ``group`` holds bit-identical ``tensors`` (one small all-gather)."""
+    d = replica_checksum(tensors)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return True
+    out = [torch.empty_like(d) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, d, group=group)
+    return all(bool(torch.equal(o, out[0])) for o in out)

@@ -96,16 +96,25 @@ def make_surface(_C) -> SimpleNamespace:
                 s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, grad_color, grad_depth, grad_alpha, sh,
                 s.sh_degree, s.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, alpha, s.debug,
             )
-            if s.debug:
-                cpu_args = cpu_deep_copy_tuple(args)
-                try:
+            # a gradient sink (dp.GradientBucket) hands its views to ONE backward per step when
+            # autograd is the caller: autograd sums the results of several backwards itself
+            tracks = hasattr(_C, "in_autograd")
+            if tracks:
+                _C.in_autograd = True
+            try:
+                if s.debug:
+                    cpu_args = cpu_deep_copy_tuple(args)
+                    try:
+                        grads = _C.rasterize_gaussians_backward(*args)
+                    except Exception as ex:
+                        torch.save(cpu_args, "snapshot_bw.dump")
+                        print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                        raise ex
+                else:
                     grads = _C.rasterize_gaussians_backward(*args)
-                except Exception as ex:
-                    torch.save(cpu_args, "snapshot_bw.dump")
-                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                    raise ex
-            else:
-                grads = _C.rasterize_gaussians_backward(*args)
+            finally:
+                if tracks:
+                    _C.in_autograd = False
             (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
              grad_scales, grad_rotations) = grads
             # one gradient per forward input (…/__init__.py:146-158)

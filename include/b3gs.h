@@ -167,6 +167,27 @@ B3GS_API int b3gs_backward(
     int debug,
     void* stream);
 
+/*
+ * b3gs_backward with option flags (an addition; b3gs_backward == flags 0):
+ *   B3GS_BWD_ACCUMULATE  the five parameter gradients a trainer sums over the views of one
+ *       step — dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale, dL_drot — are ADDED to the values
+ *       already in those buffers instead of overwriting them (the reference's binocular step
+ *       renders two views before one optimizer step, train.py:100,128; with this flag the
+ *       second view's backward accumulates straight into the data-parallel exchange bucket).
+ *       The per-view outputs (dL_dmean2D, dL_dconic, dL_dcolor, dL_ddepth, dL_dcov3D) are
+ *       written as usual.
+ */
+#define B3GS_BWD_ACCUMULATE 1u
+B3GS_API int b3gs_backward_flags(
+    unsigned flags,
+    int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
+    const float* shs, const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+    char* image_buffer, const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+    float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream);
+
 /* Visibility mask.  Replaces Rasterizer::markVisible (rasterizer.h:24-29,
  * rasterizer_impl.cu:54-66,141-153): present[i] = (z_view > 0.2). `present` is
  * bool[P] (1 byte each). */

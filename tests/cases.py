@@ -26,7 +26,7 @@ def load_golden(name):
 
 
 def make_case(name):
-    from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene
+    from workloads import make_camera, make_pixel_grads, make_scene
     spec = CASES[name]
     scene = make_scene(**spec["scene"])
     cam = make_camera(**spec["cam"])

@@ -7,7 +7,7 @@ container):
     cp gpurun_out/golden/*.npz tests/golden/
 
 Each fixture records a seeded synthetic case (regenerated from the stored parameters by
-``binocular3dgs_b200.synthetic``, so inputs are not stored) and the outputs of
+``workloads``, so inputs are not stored) and the outputs of
 oracle/_ref/libdgr_ref.so — the unmodified reference kernels compiled from
 /root/reference — for that case: radii, depth bits, tiles_touched, the sorted
 point_list, per-tile ranges, n_contrib, the three images and all gradients.  The CPU
@@ -24,7 +24,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import make_camera, make_pixel_grads, make_scene  # noqa: E402
 from oracle import refbackend  # noqa: E402
 import util  # noqa: E402
 

@@ -8,7 +8,7 @@ C-ABI (ctypes -> libb3gs.so).  Three checkers, in decreasing strictness:
 Bars: bit-exact for radii, depth bits, tiles_touched, R, the sorted point_list,
 ranges, n_contrib; images <= 1e-5 max-abs (they are in fact bit-identical to the
 reference, asserted where the reference is available); gradients within
-max(20 x the reference's measured run-to-run spread, 5e-5) of tensor scale.
+max(6 x the reference's measured run-to-run spread, 2e-5) of tensor scale.
 """
 import numpy as np
 import pytest
@@ -16,7 +16,7 @@ import torch
 
 import cases
 import util
-from binocular3dgs_b200.synthetic import CONFIGS, Scene, make_camera, make_pixel_grads, make_scene
+from workloads import CONFIGS, Scene, make_camera, make_pixel_grads, make_scene
 
 pytestmark = pytest.mark.gpu
 GRAD_KEYS = ("g_means3D", "g_means2D", "g_scales", "g_rotations", "g_opacities", "g_shs")
@@ -71,13 +71,13 @@ def test_native_vs_golden(name, nat, dev):
     out = util.surface_forward_backward(nat, scene, cam, bg_t, tuple(t.to(dev) for t in grads), scale_modifier=sm)
     spread = dict(zip(sorted(GRAD_KEYS), g["grad_spread"]))
     for k in GRAD_KEYS:
-        tol = max(20 * spread[k], 5e-5)
+        tol = max(6 * spread[k], 2e-5)
         err = util.rel_err(out[k].cpu(), torch.from_numpy(g[k]))
         assert err <= tol, (k, err, tol)
 
 
 # ------------------------------------------------------------------ live reference
-@pytest.mark.parametrize("cfg,kind", [("plumbing", "cube"), ("lego", "cube"), ("lego", "shell"), ("fern", "cube")])
+@pytest.mark.parametrize("cfg,kind", [("plumbing", "cube"), ("lego", "cube"), ("lego", "shell"), ("fern", "cube"), ("dtu", "cube")])
 def test_native_vs_reference_kernels(cfg, kind, nat, ref, dev):
     c = CONFIGS[cfg]
     W, H, P = c["width"], c["height"], c["P"]
@@ -101,8 +101,8 @@ def test_native_vs_reference_kernels(cfg, kind, nat, ref, dev):
     gr = util.surface_forward_backward(ref, scene, cam, bg, grads)
     gr2 = util.surface_forward_backward(ref, scene, cam, bg, grads)
     for k in GRAD_KEYS:
-        tol = max(20 * util.rel_err(gr2[k], gr[k]), 5e-5)
-        assert util.rel_err(gn[k], gr[k]) <= tol, k
+        tol = max(6 * util.rel_err(gr2[k], gr[k]), 2e-5)
+        assert util.rel_err(gn[k], gr[k]) <= tol, (k, util.rel_err(gn[k], gr[k]), tol)
 
 
 # ------------------------------------------------------------------ CPU oracle
@@ -368,7 +368,7 @@ def test_unused_outputs_pass_null_gradients_and_match_explicit_zeros():
     C-ABI (no materialised zero images) and give the same result as explicit zeros."""
     from binocular3dgs_b200 import _backend
     from binocular3dgs_b200.rasterizer import make_surface
-    from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene
+    from workloads import make_camera, make_pixel_grads, make_scene
     dev = torch.device("cuda:0")
     scene, cam = make_scene(3000, seed=12).to(dev), make_camera(120, 90).to(dev)
     bg = torch.zeros(3, device=dev)

@@ -10,7 +10,7 @@ import pytest
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
-from binocular3dgs_b200.synthetic import make_camera, make_scene
+from workloads import make_camera, make_scene
 from oracle import cpu_oracle as orc
 
 C0 = 0.28209479177387814
@@ -79,7 +79,7 @@ def test_pinhole_projection_by_hand():
     # identity camera at the origin looking down +z: pixel = ((x/z * f) + W/2) - 0.5
     W, H, fov = 64, 48, 0.9
     V = np.eye(4, dtype=np.float32)
-    from binocular3dgs_b200.synthetic import _projection
+    from workloads import _projection
     fovy = 2 * math.atan(H / (2 * (W / (2 * math.tan(fov / 2)))))
     Pm = (V @ _projection(0.01, 100.0, fov, fovy).numpy().T).astype(np.float32)  # transposed convention
     means = np.array([[0.0, 0.0, 2.0], [0.3, -0.2, 3.0], [0.0, 0.0, 0.1]], np.float32)

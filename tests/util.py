@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from binocular3dgs_b200.rasterizer import GaussianRasterizationSettings, make_surface
-from binocular3dgs_b200.synthetic import Camera, Scene
+from workloads import Camera, Scene
 
 
 def settings_for(cam: Camera, bg: torch.Tensor, sh_degree: int, scale_modifier=1.0, debug=False):

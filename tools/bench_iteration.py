@@ -44,7 +44,7 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
     import bench_loss
     from binocular3dgs_b200 import _backend, binocular, losses, parameters
     from binocular3dgs_b200.rasterizer import GaussianRasterizationSettings, make_surface
-    from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_scene
+    from workloads import CONFIGS, make_camera, make_scene
 
     cfg = CONFIGS[config]
     W, H, P = cfg["width"], cfg["height"], cfg["P"]

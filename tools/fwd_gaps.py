@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402
 from binocular3dgs_b200 import _backend  # noqa: E402
-from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_scene  # noqa: E402
+from workloads import CONFIGS, make_camera, make_scene  # noqa: E402
 
 dev = torch.device("cuda:0")
 name = sys.argv[1] if len(sys.argv) > 1 else "lego"

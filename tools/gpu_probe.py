@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from binocular3dgs_b200 import _backend  # noqa: E402
-from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
 from oracle import cpu_oracle as orc  # noqa: E402
 from oracle import refbackend  # noqa: E402
 import util  # noqa: E402

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from binocular3dgs_b200 import _backend  # noqa: E402
-from binocular3dgs_b200.synthetic import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import CONFIGS, make_camera, make_pixel_grads, make_scene  # noqa: E402
 import util  # noqa: E402
 
 which, name, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402
 from binocular3dgs_b200 import _backend, losses, parameters  # noqa: E402
 from binocular3dgs_b200.rasterizer import make_surface  # noqa: E402
-from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import make_camera, make_pixel_grads, make_scene  # noqa: E402
 
 dev = torch.device("cuda:0")
 scene, cam = make_scene(2000, seed=1).to(dev), make_camera(64, 64).to(dev)

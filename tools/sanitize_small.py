@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402
 from binocular3dgs_b200 import _backend, binocular, losses, parameters  # noqa: E402
 from binocular3dgs_b200.simple_knn import distCUDA2  # noqa: E402
-from binocular3dgs_b200.synthetic import make_camera, make_pixel_grads, make_scene  # noqa: E402
+from workloads import make_camera, make_pixel_grads, make_scene  # noqa: E402
 
 dev = torch.device("cuda:0")
 nat = _backend.native()
