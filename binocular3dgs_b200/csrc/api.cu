@@ -36,7 +36,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- blob layouts: pure functions of (P), (R), (W,H) --------------------------
 struct GeomLayout {
-    size_t records, depths, tiles_touched, sorted_ids, point_offsets, clamped, counter, grads, scratch, total;
+    size_t records, depths, tiles_touched, sorted_ids, point_offsets, clamped, rects, counter, grads, scratch, total;
     explicit GeomLayout(int P) {
         const size_t p = (size_t)(P > 0 ? P : 0);
         size_t o = 0;
@@ -46,6 +46,7 @@ struct GeomLayout {
         sorted_ids = o;    o = align_up(o + p * 4, 256);   // Gaussian ids in (depth bits, id) order
         point_offsets = o; o = align_up(o + p * 4, 256);   // exclusive scan of tiles_touched in that order
         clamped = o;       o = align_up(o + p, 256);
+        rects = o;         o = align_up(o + p * 8, 256);   // tile rectangles {x0|y0<<16, w|h<<16}
         counter = o;       o = align_up(o + 16, 256);      // R accumulated by the preprocess
         grads = o;         o = align_up(o + p * B3_GRAD_STRIDE * 4, 256);
         // Phase-1 sort scratch is dead once the forward returns; the backward's packed
@@ -65,14 +66,18 @@ struct ImageLayout {
         total = o + 256;
     }
 };
+// point_list sits at offset 0 and is all the backward reads, so the backward re-derives what
+// it needs from R alone; the forward's scratch behind it depends on the algorithm
+// (binning.cu): on (P, tile grid) for the direct tile binning, on R for the radix fallback.
 struct BinLayout {
     size_t point_list, scratch, scratch_bytes, total;
-    explicit BinLayout(int R, bool with_scratch = true) {
+    explicit BinLayout(int R) : BinLayout(R, 0, 0, 0, false) {}
+    BinLayout(int R, int P, int grid_x, int grid_y, bool with_scratch = true) {
         const size_t r = (size_t)(R > 0 ? R : 0);
         size_t o = 0;
         point_list = o; o = align_up(o + r * 4, 256);
         scratch = o;
-        scratch_bytes = with_scratch ? binning_phase2_scratch_bytes(R) : 0;
+        scratch_bytes = with_scratch ? binning_phase2_scratch_bytes(P, R, grid_x, grid_y) : 0;
         o = align_up(o + scratch_bytes, 256);
         total = o + 256;
     }
@@ -224,6 +229,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         pa.depths = reinterpret_cast<float*>(geo + gl.depths);
         pa.tiles_touched = reinterpret_cast<uint32_t*>(geo + gl.tiles_touched);
         pa.clamped = reinterpret_cast<uint8_t*>(geo + gl.clamped);
+        pa.rects = reinterpret_cast<uint2*>(geo + gl.rects);
         pa.num_rendered = reinterpret_cast<uint32_t*>(geo + gl.counter);
         // counter words: [0] R = 0, [1] OR of depth keys = 0, [2] AND of depth keys = ~0
         cudaError_t e = cudaMemsetAsync(pa.num_rendered, 0, 2 * sizeof(uint32_t), st);
@@ -252,6 +258,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
             b1.key_bits = pa.num_rendered + 1;
             b1.sorted_ids = reinterpret_cast<uint32_t*>(geo + gl.sorted_ids);
             b1.sorted_offsets = reinterpret_cast<uint32_t*>(geo + gl.point_offsets);
+            b1.need_offsets = binning_uses_tile_bins(P, grid_x, grid_y) ? 0 : 1;
             b1.scratch = geo + gl.scratch;
             StageTimer t_(ST_SCAN, st);
             e = run_binning_phase1(b1, st);
@@ -264,7 +271,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         R = *hw;
     }
 
-    BinLayout bl(R);
+    BinLayout bl(R, P, grid_x, grid_y);
     char* bin = static_cast<char*>(binning.resize(binning.user, bl.total));
     if (!bin && bl.total > 0) return fail(B3GS_ERR_ALLOC, "b3gs_forward: binning buffer allocation failed");
     bin = align_ptr(bin);
@@ -278,6 +285,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         ba.radii = radii;
         ba.sorted_ids = reinterpret_cast<const uint32_t*>(geo + gl.sorted_ids);
         ba.sorted_offsets = reinterpret_cast<const uint32_t*>(geo + gl.point_offsets);
+        ba.rects = reinterpret_cast<const uint2*>(geo + gl.rects);
         ba.point_list = point_list;
         ba.ranges = ranges;
         ba.scratch = bin + bl.scratch;
@@ -330,7 +338,7 @@ int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float*
 
     GeomLayout gl(P);
     ImageLayout il(width, height);
-    BinLayout bl(R, /*with_scratch=*/false);
+    BinLayout bl(R);
     char* geo = align_ptr(geom_buffer);
     char* img = align_ptr(image_buffer);
     char* bin = binning_buffer ? align_ptr(binning_buffer) : nullptr;
@@ -414,6 +422,9 @@ int b3gs_mark_visible(int P, const float* means3D, const float* viewmatrix, cons
 
 size_t b3gs_geometry_bytes(int P) { return GeomLayout(P).total; }
 size_t b3gs_binning_bytes(int R) { return BinLayout(R).total; }
+size_t b3gs_binning_bytes_forward(int P, int R, int width, int height) {
+    return BinLayout(R, P, (width + B3_TILE_X - 1) / B3_TILE_X, (height + B3_TILE_Y - 1) / B3_TILE_Y).total;
+}
 size_t b3gs_image_bytes(int width, int height) { return ImageLayout(width, height).total; }
 
 size_t b3gs_geometry_offset(int P, const char* name) {
@@ -424,6 +435,7 @@ size_t b3gs_geometry_offset(int P, const char* name) {
     if (!strcmp(name, "point_offsets")) return l.point_offsets;
     if (!strcmp(name, "sorted_ids")) return l.sorted_ids;
     if (!strcmp(name, "clamped")) return l.clamped;
+    if (!strcmp(name, "rects")) return l.rects;
     if (!strcmp(name, "grads")) return l.grads;
     return (size_t)-1;
 }

@@ -13,7 +13,13 @@
 //   phase 1 (P-sized, runs while the host waits for R):
 //     stable LSD sort of the P Gaussians by float_bits(depth)        4 x 8-bit passes
 //     exclusive scan of tiles_touched in that order                   -> emission offsets
-//   phase 2 (R-sized):
+//   phase 2 (R-sized), default — direct tile binning, ONE pass over the instances:
+//     count   per (batch of depth-consecutive Gaussians, tile) instance counts     table[nb][T]
+//     scan    along the batches per tile, then over the tiles                      -> ranges
+//     scatter every batch walks its Gaussians in depth order with the tile counters in
+//             shared memory (loaded by one TMA bulk copy) and stores each id at its final
+//             position: 4 B written per instance, nothing else R-sized is touched
+//   phase 2, fallback (tile grid wider than kBandTilesMax; B3GS_BINNING=radix):
 //     emit (tile, id) instances in depth order, one warp per 32 Gaussians
 //     stable LSD sort of the instances by tile id                     ceil(bits(T)/8) passes
 //     tile ranges from the sorted tile ids
@@ -453,6 +459,7 @@ struct Phase1Args {
     const uint32_t* key_bits;  // [0] OR, [1] AND of the visible depth keys
     uint32_t *keysB, *keysC, *valsA, *valsB, *hist, *totals, *sums;
     uint32_t *sorted_ids, *sorted_offsets;
+    int need_offsets;
 };
 
 // Up to this many radix tiles each block derives its own offsets straight from the
@@ -558,6 +565,7 @@ __global__ void __launch_bounds__(kRadixThreads, 2) depth_sort_coop(Phase1Args a
         for (int j = blockIdx.x * kRadixThreads + tid; j < n; j += gridDim.x * kRadixThreads) a.sorted_ids[j] = (uint32_t)j;
         grid.sync();
     }
+    if (!a.need_offsets) return;  // grid-uniform: the direct tile binning derives its own offsets
     // exclusive scan of tiles_touched in depth order -> emission offsets
     const int nt = (n + kScanTile - 1) / kScanTile;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -654,6 +662,7 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
         k.keysB = keysB; k.keysC = keysC; k.valsA = valsA; k.valsB = valsB;
         k.hist = hist; k.totals = hist + (size_t)kRadixBins * depth_blocks(a.P); k.sums = sums;
         k.sorted_ids = a.sorted_ids; k.sorted_offsets = a.sorted_offsets;
+        k.need_offsets = a.need_offsets;
         // at least 32 blocks so that the 256 digit rows find 256 warps
         int grid = depth_blocks(a.P) < 32 ? 32 : depth_blocks(a.P);
         if (grid > limit) grid = limit;
@@ -673,7 +682,7 @@ cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream) 
     radix_pass<uint32_t>(keysC, valsB, keysB, valsA, hist, totals, a.P, 16, false, stream);
     radix_pass<uint32_t>(keysB, valsA, keysC, a.sorted_ids, hist, totals, a.P, 24, false, stream);
     // emission offsets in depth order
-    exclusive_scan_gather(a.tiles_touched, a.sorted_ids, a.sorted_offsets, sums, nullptr, a.P, stream);
+    if (a.need_offsets) exclusive_scan_gather(a.tiles_touched, a.sorted_ids, a.sorted_offsets, sums, nullptr, a.P, stream);
     return cudaGetLastError();
 }
 
@@ -792,6 +801,301 @@ static int tile_passes(int T) {
     return bits <= 8 ? 1 : (bits <= 16 ? 2 : (bits <= 24 ? 3 : 4));
 }
 
+
+// ------------------------------------------------------------------ phase 2: direct tile binning
+// (large tile grids only, see binning_uses_tile_bins)
+// The instance stream in depth order is never materialised.  The P depth-ordered Gaussians
+// are cut into nb batches of B; a BLOCK of 8 warps owns a batch, warp w the w-th eighth of it
+// (still in depth order).  Final position of instance (g, tile) =
+//   tile_start[tile] + #instances of `tile` in earlier batches          (table[b][tile], scanned)
+//                    + #instances of `tile` in earlier warps of the block (wcount[b][warp][tile], u8)
+//                    + rank among the warp's own Gaussians,
+// and the last term is what the warp's private per-tile counter holds when the warp reaches
+// g, because a warp walks its Gaussians in depth order and the tiles of one Gaussian are
+// distinct (lanes = tiles of the current rectangle: no two lanes touch the same counter).
+//   count:   per-warp counters -> wcount (one byte each), summed over the block -> table[b][.]
+//   scan:    table[b][t] <- tile_start[t] + sum_{b' < b} table[b'][t]   (three small kernels)
+//   scatter: prefix of wcount over the 8 warps on top of table[b][.], then every instance
+//            does  pos = counter[warp][tile]++ ; point_list[pos] = id.
+// The image is cut into BANDS of whole tile rows (<= kBandTilesMax tiles) and a block makes
+// one pass over its batch per band with only that band's counters in shared memory.  Why,
+// all measured on B200 at 1M Gaussians / 1600x1200 / 42M instances (profiles/README.md r02c-d):
+//  (i)  one warp walking 512 Gaussians against all T counters is a 28 000-instruction dependent
+//       chain at 7 warps per SM — 230 us for the count alone; eight short chains per block
+//       and four blocks per SM hide most of that latency (156 us);
+//  (ii) written in depth order, every 32-byte sector of the output stays half-written for the
+//       lifetime of a batch, the open sectors of ~1000 concurrent batches (85 MB) do not fit
+//       the L2 and each is evicted and re-fetched (1.8 GB of DRAM traffic for a 169 MB list,
+//       1.05 ms).  Band by band, all blocks write the same narrow region at about the same
+//       time and most sectors complete while resident (0.38 GB, 0.46 ms);
+//  (iii) an instance-parallel variant (lane = Gaussian, per-tile chunk masks for the rank)
+//       loses to lane divergence over the rectangle sizes: 1.37 ms.
+// What remains is the dependent walk and the 4-byte scattered store itself (~110 G stores/s):
+// depth sort + binning 0.677 ms against 0.777 ms for emit + two radix passes at 42 instances
+// per Gaussian (1M / 1600x1200), 0.126 against 0.141 ms at 16 (200k / 800x800).  Bit-identical
+// output either way: a stable distribution by tile of a (depth, id)-ordered sequence.
+constexpr int kBinChunk = 32;            // batches per scan chunk
+constexpr int kBinWarps = 8;             // warps per block = sub-batches per batch
+constexpr int kBandTilesMax = 1152;      // counters of one band: 8 x 4.5 KB of shared memory (4 blocks per SM)
+constexpr int kBandRowsMax = 200;        // rows of a band (the lane map stores a row in 8 bits)
+constexpr int kMaxBinBatch = 1024;       // Gaussians per batch: 128 per warp (one-byte counts hold <= 255)
+constexpr int kMinBinTiles = 0;          // smaller grids would go through emit + radix (none: the direct path wins or ties at all BASELINE sizes)
+
+struct TileBinArgs {
+    int P, B, nb, T, T_pad, grid_x, grid_y, band_rows;
+    uint32_t cap;                 // point_list capacity (instances)
+    const uint32_t* sorted_ids;
+    const uint2* rects;
+    uint32_t* table;              // [nb][T_pad]
+    uint8_t* wcount;              // [nb][kBinWarps][T_pad]
+    uint32_t* point_list;
+};
+
+// Batch size: 512 / 1024 Gaussians per block (64 / 128 per warp) give 400-1000 blocks at the
+// BASELINE sizes; doubled while the table would outweigh the instance list itself (many tiles, few
+// instances).  B3GS_BIN_BATCH overrides (tuning).
+static int bin_batch_size(int P, int R, int T_pad) {
+    static const int forced = [] { const char* e = getenv("B3GS_BIN_BATCH"); return e ? atoi(e) : 0; }();
+    if (forced >= 256 && forced <= kMaxBinBatch && (forced & (forced - 1)) == 0) return forced;
+    int B = P >= (1 << 19) ? 1024 : 512;   // measured: 1M Gaussians 0.593 vs 0.642 ms, 200k 0.088 vs 0.117 ms
+    const size_t budget = (size_t)(R > 0 ? R : 0) * 8 + ((size_t)32 << 20);
+    while (B < kMaxBinBatch && (size_t)((P + B - 1) / B) * T_pad * 12 > budget) B *= 2;
+    return B;
+}
+static int bin_band_rows(int grid_x, int grid_y) {
+    int r = kBandTilesMax / grid_x;
+    if (r > kBandRowsMax) r = kBandRowsMax;
+    if (r > grid_y) r = grid_y;
+    return r < 1 ? 1 : r;
+}
+// shared memory of one block: per-warp band counters, the batch's rectangle staging
+// (x0|y0<<16, w|h<<16, id), the lane map
+static size_t bin_smem_bytes(int B) {
+    return (size_t)kBinWarps * kBandTilesMax * 4 + (size_t)B * 12 + 33 * 32 * 4;
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x;
+    uint32_t* s_cnt = smem;                                  // [kBinWarps][kBandTilesMax]
+    uint32_t* s_xy = smem + kBinWarps * kBandTilesMax;       // B
+    uint32_t* s_wh = s_xy + a.B;                             // B
+    uint32_t* s_id = s_wh + a.B;                             // B
+    uint32_t* s_map = s_id + a.B;                            // [33][32]: row | column << 8 | rows per step << 16
+    uint32_t* row = a.table + (size_t)b * a.T_pad;
+    uint8_t* wrow = a.wcount + (size_t)b * kBinWarps * a.T_pad;
+    uint32_t* cnt = s_cnt + warp * kBandTilesMax;            // this warp's counters
+
+    // lane map: for a rectangle bw tiles wide, lane L handles column L % bw of rows
+    // L / bw, L / bw + rows, ... with rows = 32 / bw whole rows per step (255: lane idle)
+    for (int bw = 1 + warp; bw <= 32; bw += kBinWarps) {
+        const int rows = 32 / bw, ry = lane / bw;
+        s_map[bw * 32 + lane] = (ry < rows ? (uint32_t)ry : 255u) | ((uint32_t)(lane - ry * bw) << 8) | ((uint32_t)rows << 16);
+    }
+    // stage the batch: rectangles (and ids) in depth order
+    const int i0 = b * a.B, n = min(a.P, i0 + a.B) - i0;
+    for (int k = threadIdx.x; k < n; k += 32 * kBinWarps) {
+        const uint32_t g = __ldg(a.sorted_ids + i0 + k);
+        const uint2 r = __ldg(a.rects + g);
+        s_xy[k] = r.x; s_wh[k] = r.y;
+        if (kScatter) s_id[k] = g;
+    }
+    const int sub = a.B / kBinWarps;                          // Gaussians per warp
+    const int w0 = warp * sub, w1 = min(n, w0 + sub);
+
+    for (int by0 = 0; by0 < a.grid_y; by0 += a.band_rows) {
+        const int by1 = min(a.grid_y, by0 + a.band_rows);
+        const int band_start = by0 * a.grid_x, band_tiles = (by1 - by0) * a.grid_x;
+        if (kScatter) {
+            // start positions: table[b][tile] + the counts of the earlier warps
+            for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) {
+                uint32_t run = __ldg(row + band_start + k);
+#pragma unroll
+                for (int w = 0; w < kBinWarps; w++) {
+                    s_cnt[w * kBandTilesMax + k] = run;
+                    run += __ldg(wrow + (size_t)w * a.T_pad + band_start + k);
+                }
+            }
+        } else {
+            for (int w = 0; w < kBinWarps; w++)
+                for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) s_cnt[w * kBandTilesMax + k] = 0u;
+        }
+        __syncthreads();  // counters initialised (and, first band, the staging complete)
+
+        for (int c = w0; c < w1; c += 32) {
+            // 32 Gaussians at once: clip to the band, precompute what the serial part needs
+            uint32_t t0 = 0u, wh = 0u, g = 0u;
+            if (c + lane < w1) {
+                const uint32_t xy = s_xy[c + lane], w2 = s_wh[c + lane];
+                const int y0 = (int)(xy >> 16), y1 = y0 + (int)(w2 >> 16);
+                const int cy0 = max(y0, by0), cy1 = min(y1, by1);
+                if (w2 != 0u && cy1 > cy0) {
+                    t0 = (uint32_t)((cy0 - by0) * a.grid_x) + (xy & 0xffffu);
+                    wh = (w2 & 0xffffu) | ((uint32_t)(cy1 - cy0) << 16);
+                    if (kScatter) g = s_id[c + lane];
+                }
+            }
+            unsigned nz = __ballot_sync(full, wh != 0u);
+            while (nz) {
+                const int src = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t bt0 = __shfl_sync(full, t0, src), bwh = __shfl_sync(full, wh, src);
+                const uint32_t bg = kScatter ? __shfl_sync(full, g, src) : 0u;
+                const int bw = (int)(bwh & 0xffffu), bh = (int)(bwh >> 16);
+                if (bw <= 32) {
+                    const uint32_t m = s_map[bw * 32 + lane];
+                    const int rows = (int)(m >> 16);
+                    uint32_t* pc = cnt + bt0 + ((m >> 8) & 0xffu);
+                    for (int y = (int)(m & 0xffu); y < bh; y += rows) {
+                        const uint32_t pos = pc[y * a.grid_x];
+                        pc[y * a.grid_x] = pos + 1u;
+                        if (kScatter && pos < a.cap) a.point_list[pos] = bg;
+                    }
+                } else {
+                    for (int y = 0; y < bh; y++) {
+                        for (int x = lane; x < bw; x += 32) {
+                            uint32_t* q = cnt + bt0 + y * a.grid_x + x;
+                            const uint32_t pos = *q;
+                            *q = pos + 1u;
+                            if (kScatter && pos < a.cap) a.point_list[pos] = bg;
+                        }
+                    }
+                }
+                __syncwarp();  // the next Gaussian may touch the same counters
+            }
+        }
+        __syncthreads();  // every warp's counts are final / every warp has emitted
+        if (!kScatter) {
+            // per-warp counts (one byte: a warp owns <= 255 Gaussians) and the block total -> global
+            for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int w = 0; w < kBinWarps; w++) {
+                    const uint32_t v = s_cnt[w * kBandTilesMax + k];
+                    wrow[(size_t)w * a.T_pad + band_start + k] = (uint8_t)v;
+                    sum += v;
+                }
+                row[band_start + k] = sum;
+            }
+            __syncthreads();  // counters free for the next band
+        }
+    }
+}
+
+// chunk_sums[c][t] = sum of table[b][t] over the batches of chunk c; tile_total[t] += that
+__global__ void __launch_bounds__(256) bin_chunk_sums(const uint32_t* __restrict__ table, int nb, int T, int T_pad,
+                                                     uint32_t* __restrict__ chunk_sums,
+                                                     uint32_t* __restrict__ tile_total) {
+    const int t = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+    if (t >= T) return;
+    const int b0 = c * kBinChunk, b1 = min(nb, b0 + kBinChunk);
+    uint32_t s = 0;
+#pragma unroll 8
+    for (int b = b0; b < b1; b++) s += __ldg(table + (size_t)b * T_pad + t);
+    chunk_sums[(size_t)c * T_pad + t] = s;
+    if (s) atomicAdd(tile_total + t, s);
+}
+
+// exclusive scan of the tile totals -> tile_start (in place) and ranges ((0,0) for empty tiles,
+// as the reference's memset + identifyTileRanges leave them)
+__global__ void __launch_bounds__(1024) bin_tile_scan(uint32_t* __restrict__ tile_total, int T, uint2* __restrict__ ranges) {
+    __shared__ uint32_t s_warp[32];
+    uint32_t carry = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const uint32_t v = t < T ? tile_total[t] : 0u;
+        uint32_t total;
+        const uint32_t inc = block_inclusive_scan(v, s_warp, total);
+        if (t < T) {
+            const uint32_t start = carry + inc - v;
+            tile_total[t] = start;
+            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        }
+        carry += total;
+    }
+}
+
+// table[b][t] <- tile_start[t] + (instances of t in earlier batches)
+__global__ void __launch_bounds__(256) bin_apply(uint32_t* __restrict__ table, int nb, int T, int T_pad,
+                                                const uint32_t* __restrict__ chunk_sums,
+                                                const uint32_t* __restrict__ tile_start) {
+    const int t = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+    if (t >= T) return;
+    uint32_t run = tile_start[t];
+    for (int k = 0; k < c; k++) run += __ldg(chunk_sums + (size_t)k * T_pad + t);
+    const int b0 = c * kBinChunk, b1 = min(nb, b0 + kBinChunk);
+    uint32_t v[kBinChunk];
+#pragma unroll
+    for (int k = 0; k < kBinChunk; k++) v[k] = b0 + k < b1 ? table[(size_t)(b0 + k) * T_pad + t] : 0u;
+#pragma unroll
+    for (int k = 0; k < kBinChunk; k++) {
+        if (b0 + k < b1) table[(size_t)(b0 + k) * T_pad + t] = run;
+        run += v[k];
+    }
+}
+
+static bool use_radix() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B3GS_BINNING");
+        v = (e && !strcmp(e, "radix")) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+struct TileBinLayout {
+    int B, nb, nchunks, T, T_pad, band_rows;
+    size_t table, wcount, chunk_sums, tile_total, total;
+    TileBinLayout(int P, int R, int grid_x, int grid_y) {
+        T = grid_x * grid_y;
+        T_pad = (T + 3) & ~3;
+        B = bin_batch_size(P, R, T_pad);
+        band_rows = bin_band_rows(grid_x, grid_y);
+        nb = P > 0 ? (P + B - 1) / B : 0;
+        nchunks = (nb + kBinChunk - 1) / kBinChunk;
+        size_t o = 0;
+        table = o;      o = align_up(o + (size_t)nb * T_pad * 4, 256);
+        wcount = o;     o = align_up(o + (size_t)nb * kBinWarps * T_pad, 256);
+        chunk_sums = o; o = align_up(o + (size_t)nchunks * T_pad * 4, 256);
+        tile_total = o; o = align_up(o + (size_t)T_pad * 4, 256);
+        total = o;
+    }
+};
+
+static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t stream) {
+    const TileBinLayout L(a.P, a.R, a.grid_x, a.grid_y);
+    uint32_t* table = reinterpret_cast<uint32_t*>(q + L.table);
+    uint32_t* chunk_sums = reinterpret_cast<uint32_t*>(q + L.chunk_sums);
+    uint32_t* tile_total = reinterpret_cast<uint32_t*>(q + L.tile_total);
+    const size_t smem = bin_smem_bytes(L.B);
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != attr_dev) {  // opt in to more than 48 KB of dynamic shared memory, once per device
+        cudaFuncSetAttribute(tile_bins_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(tile_bins_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_dev = dev;
+    }
+    TileBinArgs k;
+    k.P = a.P; k.B = L.B; k.nb = L.nb; k.T = L.T; k.T_pad = L.T_pad; k.grid_x = a.grid_x; k.grid_y = a.grid_y;
+    k.band_rows = L.band_rows;
+    k.cap = (uint32_t)a.R;
+    k.sorted_ids = a.sorted_ids; k.rects = a.rects; k.table = table; k.point_list = a.point_list;
+    k.wcount = reinterpret_cast<uint8_t*>(q + L.wcount);
+    cudaError_t e = cudaMemsetAsync(tile_total, 0, (size_t)L.T_pad * 4, stream);
+    if (e != cudaSuccess) return e;
+    tile_bins_kernel<false><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
+    const dim3 grid((L.T + 255) / 256, L.nchunks);
+    bin_chunk_sums<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
+    bin_tile_scan<<<1, 1024, 0, stream>>>(tile_total, L.T, a.ranges);
+    bin_apply<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
+    tile_bins_kernel<true><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
+    count_launch(5);
+    return cudaGetLastError();
+}
+
 // ---- legacy cub path (A/B only)
 __global__ void __launch_bounds__(256) emit_keys64(int P, const float4* __restrict__ records,
                                                   const float* __restrict__ depths, const int* __restrict__ radii,
@@ -852,8 +1156,17 @@ static bool use_cub() {
     return v == 1;
 }
 
-size_t binning_phase2_scratch_bytes(int R) {
+bool binning_uses_tile_bins(int P, int grid_x, int grid_y) {
+    // B3GS_BINNING=bins forces the direct path wherever it is applicable, =radix / =cub disable it
+    static const bool forced = [] { const char* e = getenv("B3GS_BINNING"); return e && !strcmp(e, "bins"); }();
+    const long long T = (long long)grid_x * grid_y;
+    return !use_cub() && !use_radix() && P > 0 && grid_x <= kBandTilesMax && grid_y < 65536 && T < (1ll << 24) &&
+           (forced || T >= kMinBinTiles);
+}
+
+size_t binning_phase2_scratch_bytes(int P, int R, int grid_x, int grid_y) {
     const size_t r = (size_t)(R > 0 ? R : 0);
+    if (binning_uses_tile_bins(P, grid_x, grid_y)) return TileBinLayout(P, R, grid_x, grid_y).total;
     if (use_cub())
         return align_up(r * 8, 256) * 2 + align_up(r * 4, 256) + align_up(cub_sort_temp_bytes(R), 256) + 256;
     // keysA[R] keysB[R] idsB[R] hist
@@ -892,7 +1205,9 @@ static cudaError_t tile_sort(const BinningPhase2Args& a, char* q, cudaStream_t s
 
 cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream) {
     const int T = a.grid_x * a.grid_y;
-    cudaError_t e = cudaMemsetAsync(a.ranges, 0, (size_t)T * sizeof(uint2), stream);
+    const bool bins = binning_uses_tile_bins(a.P, a.grid_x, a.grid_y);
+    cudaError_t e = cudaSuccess;
+    if (!bins || a.R <= 0) e = cudaMemsetAsync(a.ranges, 0, (size_t)T * sizeof(uint2), stream);  // the direct binning writes every range itself
     if (e != cudaSuccess) return e;
     if (a.R <= 0) return cudaSuccess;
     const size_t r = (size_t)a.R;
@@ -912,6 +1227,7 @@ cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream) 
         count_launch(10);
         return cudaGetLastError();
     }
+    if (bins) return tile_bins(a, q, stream);
     return T <= 65536 ? tile_sort<uint16_t>(a, q, stream) : tile_sort<uint32_t>(a, q, stream);
 }
 

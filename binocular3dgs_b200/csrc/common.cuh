@@ -94,6 +94,17 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (SASS: UBLKCP as well); dst, src and bytes multiples of 16.  The
+// generic-proxy writes to `src` must be made visible to the async proxy first.
+__device__ __forceinline__ void bulk_copy_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until the bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

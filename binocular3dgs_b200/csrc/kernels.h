@@ -31,6 +31,7 @@ struct PreprocessArgs {
     float* depths;
     uint32_t* tiles_touched;
     uint8_t* clamped;
+    uint2* rects;            // tile rectangle {x0 | y0 << 16, width | height << 16}; {0, 0} when culled
     uint32_t* num_rendered;  // device counter, zeroed by the caller; += sum(tiles_touched)
 };
 void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream);
@@ -47,6 +48,7 @@ struct BinningPhase1Args {
     const uint32_t* key_bits;       // [0] OR, [1] AND of the visible Gaussians' depth keys
     uint32_t* sorted_ids;           // out: Gaussian ids in (depth bits, id) order, P
     uint32_t* sorted_offsets;       // out: exclusive scan of tiles_touched in that order, P
+    int need_offsets;               // 0: skip that scan (the direct tile binning does not use it)
     char* scratch;
 };
 size_t binning_phase1_scratch_bytes(int P);
@@ -60,11 +62,16 @@ struct BinningPhase2Args {
     const int* radii;
     const uint32_t* sorted_ids;
     const uint32_t* sorted_offsets;
+    const uint2* rects;             // per-Gaussian tile rectangles written by the preprocess
     uint32_t* point_list;           // out: sorted Gaussian ids, R
     uint2* ranges;                  // out: per-tile [start,end), T
     char* scratch;
 };
-size_t binning_phase2_scratch_bytes(int R);
+// Which phase-2 algorithm a forward with these sizes uses: true = direct tile binning
+// (scratch is a function of P and the tile grid), false = emit + radix passes (scratch is a
+// function of R).  Phase 1 must produce sorted_offsets only for the latter.
+bool binning_uses_tile_bins(int P, int grid_x, int grid_y);
+size_t binning_phase2_scratch_bytes(int P, int R, int grid_x, int grid_y);
 cudaError_t run_binning_phase2(const BinningPhase2Args& a, cudaStream_t stream);
 
 // Stable LSD radix sort of n (key, original index) pairs on key bits [0, bits); returns

@@ -43,6 +43,7 @@ struct PreParams {
     float* depths;
     uint32_t* tiles_touched;
     uint8_t* clamped;
+    uint2* rects;
     uint32_t* num_rendered;
 };
 
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
     float4 ra = make_float4(0.f, 0.f, -1.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f),
            rc = make_float4(0.f, 0.f, 0.f, 0.f);
     uint8_t clamp_bits = 0;
+    uint2 rect = make_uint2(0u, 0u);
 
     // in_frustum (auxiliary.h:139-164): only the view-space z is live.
     const float pz = xform(V[2], V[6], V[10], V[14], x, y, z);
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
                 depth = pz;
                 radius_out = ri;
                 tiles = area;
+                rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
                 ra = make_float4(pix_x, pix_y, tau, 0.0f);
                 rb = make_float4(conx, cony, conz, op);
                 rc = make_float4(cr, cg, cbl, pz);
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
         p.tiles_touched[idx] = tiles;
         p.depths[idx] = depth;
         p.clamped[idx] = clamp_bits;
+        p.rects[idx] = rect;
         float4* rec = p.records + (size_t)idx * B3_REC_VEC4;
         rec[0] = ra; rec[1] = rb; rec[2] = rc;
     }
@@ -321,7 +325,7 @@ void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream) {
     p.focal_x = a.focal_x; p.focal_y = a.focal_y;
     p.grid_x = a.grid_x; p.grid_y = a.grid_y; p.prefiltered = a.prefiltered;
     p.radii = a.radii; p.records = a.records; p.depths = a.depths;
-    p.tiles_touched = a.tiles_touched; p.clamped = a.clamped; p.num_rendered = a.num_rendered;
+    p.tiles_touched = a.tiles_touched; p.clamped = a.clamped; p.rects = a.rects; p.num_rendered = a.num_rendered;
     preprocess_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(p);
     count_launch();
 }

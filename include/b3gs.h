@@ -199,10 +199,14 @@ B3GS_API int b3gs_mark_visible(
     unsigned char* present,
     void* stream);
 
-/* Sizes of the three opaque blobs (what the resize callbacks will be asked for).
- * Pure functions of their arguments. */
+/* Sizes of the three opaque blobs.  Pure functions of their arguments.
+ * b3gs_binning_bytes(R) is the part b3gs_backward reads (the sorted id list, at offset 0);
+ * b3gs_binning_bytes_forward is what b3gs_forward asks the binning callback for: that list
+ * plus the forward's scratch, which depends on P and the tile grid for the direct tile
+ * binning and on R for the radix fallback (binning.cu). */
 B3GS_API size_t b3gs_geometry_bytes(int P);
 B3GS_API size_t b3gs_binning_bytes(int R);
+B3GS_API size_t b3gs_binning_bytes_forward(int P, int R, int width, int height);
 B3GS_API size_t b3gs_image_bytes(int width, int height);
 
 /*
@@ -211,7 +215,8 @@ B3GS_API size_t b3gs_image_bytes(int width, int height);
  * offset, or (size_t)-1 for an unknown name.
  *   geometry: "depths" f32[P], "tiles_touched" u32[P], "point_offsets" u32[P],
  *             "records" f32[P,12] = {x, y, cull_tau, 0 | conic_x, conic_y, conic_z,
- *             opacity | r, g, b, depth}, "clamped" u8[P] (bit c = channel c clamped)
+ *             opacity | r, g, b, depth}, "clamped" u8[P] (bit c = channel c clamped),
+ *             "rects" u32[P,2] = {x0 | y0 << 16, width | height << 16} in tiles ({0,0}: culled)
  *   binning:  "point_list" u32[R]
  *   image:    "n_contrib" u32[H*W], "ranges" u32[T,2]
  */

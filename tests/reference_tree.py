@@ -25,6 +25,12 @@ REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 _cache = {}
 
 
+def _stub_attr(attr):
+    if attr.startswith("__"):          # inspect.getmodule() walks sys.modules asking for __file__ etc.
+        raise AttributeError(attr)
+    return object
+
+
 def _load_package(alias, pkg_dir):
     init = os.path.join(pkg_dir, "__init__.py")
     if not os.path.exists(init) or not any(f.startswith("_C") and f.endswith(".so") for f in os.listdir(pkg_dir)):
@@ -90,7 +96,7 @@ def render_adapter(dgr, alias):
                 assert not e.name.startswith(("diff_gaussian_rasterization", "binocular3dgs_b200", "gaussian_renderer"))
                 stub = types.ModuleType(e.name)
                 stub.__path__ = []
-                stub.__getattr__ = lambda attr: object
+                stub.__getattr__ = _stub_attr
                 sys.modules[e.name] = stub
                 for k in [k for k in sys.modules if k.split(".")[0] in ("scene", "utils", "arguments")]:
                     del sys.modules[k]
