@@ -129,9 +129,12 @@ def algorithmic_bytes(P, R, T, N, D, I_f):
     return {
         "preprocess": P * (44 + 12 * (D + 1) ** 2) + 75 * P,
         # 4 passes x (4 B hist read + 8 B read + 8 B write) + gather-scan of tiles_touched
-        "depth_sort": P * (4 * 20 + 16),
-        # emit (tile,id) 8 B + passes x 20 B + 4 B boundary scan per instance, 8 B per tile
-        "binning": 28 * P + R * (8 + 20 * (1 if T <= 256 else 2 if T <= 65536 else 3) + 4) + 8 * T,
+        # 4 passes x (4 B hist read + 8 B read + 8 B write)
+        "depth_sort": P * 4 * 20,
+        # direct tile binning (binning.cu): 4 B per instance; per (batch, tile) cell 4 B count out,
+        # 4 in (chunk sums), 8 (apply), 4 in (scatter) + 8 one-byte per-warp counts out and in;
+        # 12 B of rectangle + id per Gaussian, twice; 8 B per tile of ranges
+        "binning": 4 * R + 36 * (-(-P // (1024 if P >= (1 << 19) else 512))) * T + 24 * P + 8 * T,
         "composite_forward": 44 * I_f + 8 * T + 24 * N,
         "grad_zero": 48 * P,
         "composite_backward": 44 * I_f + 8 * T + 28 * N + 80 * I_f,
@@ -290,6 +293,75 @@ def make_step(arm, wl, bucket):
     return step
 
 
+def dp_selfcheck(arm, dev, rank, world):
+    """Correctness of the data-parallel exchange, executed by every multi-GPU bench run (the
+    driver's pytest box has one GPU): (a) b3gs_peer_allreduce against NCCL on random data,
+    (b) replicas bit-identical after the exchange, (c) gradients written by the backward
+    kernel straight into the bucket (grad sink) + exchange == the mean of the per-rank
+    gradients gathered with NCCL, (d) replicas stay bit-identical across a densification step
+    (lockstep CUDA generator + reduced statistics)."""
+    from binocular3dgs_b200 import dp
+    out = {}
+    P, M = 10007, 4
+    bucket, kind = dp.make_bucket(P, M, dev)
+    out["bucket"] = kind
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    bucket.flat.copy_(torch.randn(bucket.flat.numel(), generator=g).to(dev))
+    ref = bucket.flat.clone()
+    dist.all_reduce(ref)
+    ref /= world
+    bucket.all_reduce(average=True)
+    torch.cuda.synchronize()
+    out["peer_vs_nccl_max_rel"] = float((bucket.flat - ref).abs().max() / ref.abs().max())
+    out["replicas_identical_after_exchange"] = bool(dp.replicas_identical([bucket.flat]))
+    # (c) the real path at a small size: rank-distinct cameras, sink vs gathered
+    scene = make_scene(P, seed=5).to(dev)
+    cam = make_camera(160, 120, azimuth=0.4 + 0.7 * rank).to(dev)
+    wl = type("W", (), {})()
+    wl.scene, wl.bg, wl.H, wl.W = scene, torch.zeros(3, device=dev), 120, 160
+    wl.gc, wl.gd, wl.ga = (t.to(dev) for t in make_pixel_grads(160, 120, seed=6))
+    C = arm.C
+    C.grad_sink = None
+    o = raw_forward(C, wl, cam)
+    gr = raw_backward(C, wl, cam, o, wl.gd, wl.ga)   # (means2D, colors, opacity, means3D, cov3D, sh, scales, rot)
+    local = dict(means3D=gr[3], shs=gr[5], opacities=gr[2], scales=gr[6], rotations=gr[7])
+    gathered = {}
+    for k, v in local.items():
+        t = v.clone()
+        dist.all_reduce(t)
+        gathered[k] = t / world
+    C.grad_sink = bucket
+    try:
+        bucket.begin_step()
+        o = raw_forward(C, wl, cam)
+        raw_backward(C, wl, cam, o, wl.gd, wl.ga)
+        bucket.all_reduce(average=True)
+    finally:
+        C.grad_sink = None
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k, v in gathered.items():
+        d = float((bucket.views()[k].reshape(v.shape) - v).abs().max() / v.abs().max().clamp_min(1e-30))
+        worst = max(worst, d)
+    out["sink_exchange_vs_gathered_max_rel"] = worst
+    out["replicas_identical_gradients"] = bool(dp.replicas_identical([bucket.flat]))
+    # (d) densification in lockstep
+    dp.seed_lockstep(777)
+    xyz, scaling = scene.means3D.clone(), torch.log(scene.scales)
+    norm = gr[0][:, :2].norm(dim=-1, keepdim=True)                 # this rank's ||dL/dmean2D||
+    visible = (o[4] > 0).float().unsqueeze(1)
+    n2, v2, r2 = dp.reduce_densify_stats(norm * visible, visible, o[4])
+    sel = ((n2 / v2.clamp_min(1)).squeeze(1) >= (n2 / v2.clamp_min(1)).median())
+    std = torch.exp(scaling[sel])
+    new_xyz = torch.cat((xyz, xyz[sel] + torch.normal(torch.zeros_like(std), std)), dim=0)   # CUDA generator
+    out["densify_lockstep_identical"] = bool(dp.replicas_identical([new_xyz, r2]))
+    out["densify_cloned"] = int(sel.sum())
+    ok = (out["peer_vs_nccl_max_rel"] < 1e-5 and out["replicas_identical_after_exchange"]
+          and worst < 1e-4 and out["replicas_identical_gradients"] and out["densify_lockstep_identical"])
+    out["ok"] = bool(ok)
+    return out
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -367,6 +439,10 @@ def main():
             ms = float(t.item())
         return ms, wall, per
 
+    dp_check = dp_selfcheck(arm, dev, rank, world) if use_dp else None
+    if dp_check is not None and not dp_check["ok"]:
+        raise SystemExit("data-parallel self-check failed on rank %d: %r" % (rank, dp_check))
+
     # ---------------- the headline workload, device-resident (value)
     pair = args.config == "fern_pair"
     wl = Workload("fern" if pair else args.config, args.kind, dev, rank, pair=pair)
@@ -374,7 +450,7 @@ def main():
     bucket, bucket_kind = make_dp_bucket(wl)
     C = arm.C
     if bucket is not None:
-        C.grad_sink = bucket.views()
+        C.grad_sink = bucket             # first backward of a step overwrites, the pair's second accumulates
     step = make_step(arm, wl, bucket)
 
     sampler = ClockSampler(local_rank)
@@ -413,7 +489,10 @@ def main():
                 hv["center" + tag] = pin(cam_c.camera_center)
             host_views.append(hv)
     if arm.is_native:
-        C.grad_sink = None                          # autograd owns the gradient tensors on this path
+        # Data-parallel: the backward writes into the bucket and autograd ADOPTS those views as
+        # .grad (no pack copy); a second backward of the same step (the pair) is added by autograd
+        # in place.  Single GPU: autograd owns the gradient tensors.
+        C.grad_sink = bucket if use_dp else None
     leaves = [t.detach().clone().requires_grad_(True) for t in wl.scene.tensors()]
     h2d = sum(t.numel() * t.element_size() for t in host_views[0].values())
     d2h = 4
@@ -464,7 +543,7 @@ def main():
             t.grad = None
         loss.backward()
         if use_dp:
-            bucket.load(dict(means3D=m.grad, shs=sh.grad, opacities=o.grad, scales=s.grad, rotations=q.grad))
+            bucket.load(dict(means3D=m.grad, shs=sh.grad, opacities=o.grad, scales=s.grad, rotations=q.grad))  # no-op when adopted
             bucket.all_reduce(average=True)
         lh = loss_hosts[i & 1]
         if i >= 2:
@@ -490,7 +569,7 @@ def main():
     peak, peak_src = measured_peaks()
     if arm.is_native and prof:
         if bucket is not None:
-            C.grad_sink = bucket.views()
+            C.grad_sink = bucket
         out = step(0)
         torch.cuda.synchronize()
         R = int(out[0])
@@ -529,7 +608,7 @@ def main():
                 w2 = Workload(cname, args.kind, dev, rank, pair=cpair)
                 b2, _ = make_dp_bucket(w2)
                 if arm.is_native:
-                    C.grad_sink = b2.views() if b2 is not None else None
+                    C.grad_sink = b2
                 st2 = make_step(arm, w2, b2)
                 n2 = max(20, min(args.steps, 50))
                 ms2, _, _ = timed(st2, n2, 5)
@@ -540,6 +619,61 @@ def main():
                 configs[key] = {"error": repr(ex)}
         if arm.is_native:
             C.grad_sink = None
+
+    # ---------------- config 4's growth variant: densification-like buffer growth
+    # P grows by 10 % every 100 steps, as densify_and_prune replaces every parameter tensor by a
+    # longer one (scene/gaussian_model.py:334-345, :393); through the public API, device-resident.
+    growth = None
+    if not args.no_extra and world == 1:
+        try:
+            P0, every, n_steps = wl.P, 100, 300
+            big = make_scene(int(P0 * 1.1 ** (n_steps // every)) + 8, seed=0, kind=args.kind).to(dev)
+            torch.cuda.synchronize()
+            stats0 = torch.cuda.memory_stats(dev)
+            sizes, evs, cur, leaves_g = [], [], 0, None
+            cam0 = wl.cams[0]
+            settings = Settings(H, W, cam0.tanfovx, cam0.tanfovy, wl.bg, 1.0, cam0.world_view_transform,
+                                cam0.full_proj_transform, big.sh_degree, cam0.camera_center, False, False)
+            for i in range(n_steps):
+                Pi = int(P0 * 1.1 ** (i // every))
+                if Pi != cur:       # "densify": every tensor is re-created at the new length
+                    cur = Pi
+                    leaves_g = [t[:Pi].clone().requires_grad_(True) for t in big.tensors()]
+                m, sc, q, o, sh = leaves_g
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                means2D = torch.zeros_like(m, requires_grad=True)
+                color, radii, depth, alpha = Rasterizer(settings)(means3D=m, means2D=means2D, opacities=o, shs=sh,
+                                                                  scales=sc, rotations=q)
+                for t in leaves_g:
+                    t.grad = None
+                torch.autograd.backward([color, depth, alpha], [wl.gc, wl.gd, wl.ga])
+                b_.record()
+                evs.append((a_, b_)); sizes.append(Pi)
+            torch.cuda.synchronize()
+            ms = np.array([a_.elapsed_time(b_) for a_, b_ in evs])
+            stats1 = torch.cuda.memory_stats(dev)
+            phases = {}
+            for Pi in sorted(set(sizes)):
+                sel = ms[np.array(sizes) == Pi]
+                phases[str(Pi)] = {"median_ms": round(float(np.median(sel)), 4), "max_ms": round(float(sel.max()), 4),
+                                   "first_ms": round(float(sel[0]), 4)}
+            # a step is compared with the median of ITS size (the work itself grows with P)
+            worst = max(v["max_ms"] / v["median_ms"] for v in phases.values())
+            growth = {"what": "P += 10 %% every %d steps for %d steps (%d -> %d Gaussians), public API, fwd+bwd, "
+                              "no L2 flush" % (every, n_steps, sizes[0], sizes[-1]),
+                      "phases": phases, "worst_step_over_phase_median": round(float(worst), 3),
+                      "steps_over_1p5x_median": int(sum((ms[np.array(sizes) == int(k)] > 1.5 * v["median_ms"]).sum()
+                                                        for k, v in phases.items())),
+                      "views_per_s": round(1000.0 * n_steps / float(ms.sum()), 2),
+                      "allocator": {"cudaMalloc_calls": int(stats1.get("num_device_alloc", 0) - stats0.get("num_device_alloc", 0)),
+                                    "alloc_retries": int(stats1.get("num_alloc_retries", 0) - stats0.get("num_alloc_retries", 0)),
+                                    "reserved_MiB_before": int(stats0.get("reserved_bytes.all.current", 0)) >> 20,
+                                    "reserved_MiB_after": int(stats1.get("reserved_bytes.all.current", 0)) >> 20,
+                                    "peak_allocated_MiB": int(stats1.get("allocated_bytes.all.peak", 0)) >> 20}}
+            del big, leaves_g
+        except Exception as ex:
+            growth = {"error": repr(ex)}
 
     # ---------------- CPU baseline (oracle port), rank 0 only, bounded sample
     cpu_baseline = None
@@ -619,6 +753,10 @@ def main():
             line["kernels"] = kernels
         if configs:
             line["configs"] = configs
+        if growth:
+            line["growth"] = growth
+        if dp_check:
+            line["dp_check"] = dp_check
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if next_rows:
