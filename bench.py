@@ -634,8 +634,8 @@ def main():
             cam0 = wl.cams[0]
             settings = Settings(H, W, cam0.tanfovx, cam0.tanfovy, wl.bg, 1.0, cam0.world_view_transform,
                                 cam0.full_proj_transform, big.sh_degree, cam0.camera_center, False, False)
-            for i in range(n_steps):
-                Pi = int(P0 * 1.1 ** (i // every))
+            for i in range(-3, n_steps):          # three untimed warm-up steps at the initial size
+                Pi = int(P0 * 1.1 ** (max(i, 0) // every))
                 if Pi != cur:       # "densify": every tensor is re-created at the new length
                     cur = Pi
                     leaves_g = [t[:Pi].clone().requires_grad_(True) for t in big.tensors()]
@@ -649,7 +649,8 @@ def main():
                     t.grad = None
                 torch.autograd.backward([color, depth, alpha], [wl.gc, wl.gd, wl.ga])
                 b_.record()
-                evs.append((a_, b_)); sizes.append(Pi)
+                if i >= 0:
+                    evs.append((a_, b_)); sizes.append(Pi)
             torch.cuda.synchronize()
             ms = np.array([a_.elapsed_time(b_) for a_, b_ in evs])
             stats1 = torch.cuda.memory_stats(dev)

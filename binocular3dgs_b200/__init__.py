@@ -14,6 +14,7 @@ _surface = make_surface(_C)
 _RasterizeGaussians = _surface._RasterizeGaussians
 rasterize_gaussians = _surface.rasterize_gaussians
 GaussianRasterizer = _surface.GaussianRasterizer
+async_policy = _surface.async_policy      # rasterizer.AsyncCountPolicy: when the forward may skip its host wait
 
 __all__ = [
     "GaussianRasterizationSettings",

@@ -100,6 +100,30 @@ class Backend:
         if self._backward_flags is not None:
             self._backward_flags.argtypes = [ctypes.c_uint] + _BWD_ARGTYPES
             self._backward_flags.restype = ctypes.c_int
+        # the no-sync forward (ours only): same arguments minus `debug` and `num_rendered`, plus capacity, ticket
+        self._forward_nosync = getattr(self.lib, prefix + "forward_nosync", None)
+        if self._forward_nosync is not None:
+            self._forward_nosync.argtypes = _FWD_ARGTYPES[:-3] + [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+            self._forward_nosync.restype = ctypes.c_int
+            self._nosync_supported = g("forward_nosync_supported")
+            self._nosync_supported.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            self._nosync_supported.restype = ctypes.c_int
+            self._count_wait = g("count_wait")
+            self._count_wait.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+            self._count_wait.restype = ctypes.c_int
+        # the raw-parameter entry (ours only)
+        self._forward_raw = getattr(self.lib, prefix + "forward_raw", None)
+        if self._forward_raw is not None:
+            self._forward_raw.argtypes = ([_Buffer, _Buffer, _Buffer, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
+                                           ctypes.c_int, ctypes.c_int] + [_F] * 5 + [ctypes.c_float] + [_F] * 4 +
+                                          [ctypes.c_float, ctypes.c_float] + [_F] * 4 +
+                                          [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)])
+            self._forward_raw.restype = ctypes.c_int
+            self._backward_raw = g("backward_raw")
+            self._backward_raw.argtypes = ([ctypes.c_uint] + [ctypes.c_int] * 4 + [_F, ctypes.c_int, ctypes.c_int] +
+                                           [_F] * 5 + [ctypes.c_float] + [_F] * 5 + [ctypes.c_float, ctypes.c_float] +
+                                           [_F] * 4 + [_F] * 3 + [_F] * 7 + [ctypes.c_void_p])
+            self._backward_raw.restype = ctypes.c_int
         self._mark_visible = g("mark_visible")
         self._mark_visible.argtypes = [ctypes.c_int, _F, _F, _F, _F, ctypes.c_void_p]
         self._mark_visible.restype = ctypes.c_int
@@ -191,10 +215,27 @@ class Backend:
         return blob[off : off + nbytes].view(dtype)
 
     # ------------------------------------------------------------------ _C surface
+    def nosync_supported(self, P: int, W: int, H: int) -> bool:
+        return self._forward_nosync is not None and bool(self._nosync_supported(int(P), int(W), int(H)))
+
+    def count_wait(self, ticket: int) -> int:
+        """Block until the instance count of a no-sync forward has landed; return it."""
+        r = ctypes.c_int(0)
+        rc = self._count_wait(int(ticket), ctypes.byref(r))
+        if rc != 0:
+            raise self._err("count_wait", rc)
+        return r.value
+
+    def rasterize_gaussians_nosync(self, capacity, *args):
+        """`rasterize_gaussians` without the host wait: the binning blob holds `capacity`
+        instances and the first element of the result is a TICKET for :meth:`count_wait`
+        (include/b3gs.h: b3gs_forward_nosync).  `args` as for rasterize_gaussians."""
+        return self.rasterize_gaussians(*args, _capacity=int(capacity))
+
     def rasterize_gaussians(
         self, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-        prefiltered, debug,
+        prefiltered, debug, _capacity=None,
     ):
         if means3D.dim() != 2 or means3D.size(1) != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -220,12 +261,20 @@ class Backend:
             rendered = ctypes.c_int(0)
             stream = torch.cuda.current_stream(dev).cuda_stream
             g, b, i = self._buffers()
-            rc = self._forward(
-                g, b, i, P, int(degree), M, _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(opa), _ptr(sca),
-                float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
-                float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(), out_depth.data_ptr(),
-                out_alpha.data_ptr(), _ptr(radii), int(bool(debug)), stream, ctypes.byref(rendered),
-            )
+            if _capacity is None:
+                rc = self._forward(
+                    g, b, i, P, int(degree), M, _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(opa), _ptr(sca),
+                    float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
+                    float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(), out_depth.data_ptr(),
+                    out_alpha.data_ptr(), _ptr(radii), int(bool(debug)), stream, ctypes.byref(rendered),
+                )
+            else:   # `rendered` receives the ticket
+                rc = self._forward_nosync(
+                    g, b, i, P, int(degree), M, _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(opa), _ptr(sca),
+                    float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
+                    float(tan_fovy), int(bool(prefiltered)), out_color.data_ptr(), out_depth.data_ptr(),
+                    out_alpha.data_ptr(), _ptr(radii), stream, int(_capacity), ctypes.byref(rendered),
+                )
             if rc != 0:
                 raise self._err("rasterize_gaussians", rc)
             geom, binning, img = self._tls.slots
@@ -302,6 +351,93 @@ class Backend:
                     raise self._err("rasterize_gaussians_backward", rc)
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
+    # ------------------------------------------------------------------ raw-parameter entry
+    def rasterize_raw(self, background, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, scale_modifier,
+                      viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, degree, campos,
+                      capacity=None):
+        """b3gs_forward_raw: the reference's RAW parameters in, activations fused into the
+        preprocess.  Returns (R or ticket, color, depth, alpha, radii, geom, binning, img);
+        with ``capacity`` the forward does not wait and the first element is a ticket."""
+        if xyz.dim() != 2 or xyz.size(1) != 3:
+            raise RuntimeError("xyz must have dimensions (num_points, 3)")
+        if not xyz.is_cuda:
+            raise RuntimeError("xyz must be a CUDA tensor (no CPU path exists)")
+        P, H, W, dev = int(xyz.size(0)), int(image_height), int(image_width), xyz.device
+        M = 1 + (int(f_rest.size(1)) if f_rest is not None and f_rest.numel() else 0)
+        with torch.cuda.device(dev):
+            out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+            out_depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+            out_alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            self._tls.device = dev
+            self._tls.slots = [torch.empty(0, dtype=torch.uint8, device=dev) for _ in range(3)]
+            t = [_prep(x, n) for x, n in ((background, "background"), (xyz, "xyz"), (f_dc, "f_dc"), (f_rest, "f_rest"),
+                                          (opacity_raw, "opacity"), (scaling_raw, "scaling"), (rotation_raw, "rotation"),
+                                          (viewmatrix, "viewmatrix"), (projmatrix, "projmatrix"), (campos, "campos"))]
+            bg, m3, dc, rest, opa, sca, rot, vm, pm, cam = t
+            res = ctypes.c_int(0)
+            g, b, i = self._buffers()
+            if P == 0:
+                out_color.zero_(); out_depth.zero_(); out_alpha.zero_()
+                rc = 0
+            else:
+                rc = self._forward_raw(
+                    g, b, i, P, int(degree), M, _ptr(bg), W, H, _ptr(m3), _ptr(dc), _ptr(rest), _ptr(opa), _ptr(sca),
+                    float(scale_modifier), _ptr(rot), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx), float(tan_fovy),
+                    out_color.data_ptr(), out_depth.data_ptr(), out_alpha.data_ptr(), _ptr(radii),
+                    torch.cuda.current_stream(dev).cuda_stream, -1 if capacity is None else int(capacity),
+                    ctypes.byref(res))
+            if rc != 0:
+                raise self._err("rasterize_raw", rc)
+            geom, binning, img = self._tls.slots
+            self._tls.slots = None
+        return res.value, out_color, out_depth, out_alpha, radii, geom, binning, img
+
+    def rasterize_raw_backward(self, background, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw,
+                               scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                               dL_dout_depth, dL_dout_alpha, degree, campos, radii, geomBuffer, R, binningBuffer,
+                               imageBuffer, alphas, outputs=None, accumulate=False):
+        """b3gs_backward_raw -> (dL_dmeans2D, dL_dxyz, dL_df_dc, dL_df_rest, dL_dopacity,
+        dL_dscaling, dL_drotation), gradients of the RAW parameters.  ``outputs``: optional dict
+        name -> preallocated tensor ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+        written in place (``accumulate``: added to), e.g. slices of a dp.ParameterBucket."""
+        P, dev = int(xyz.size(0)), xyz.device
+        H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+        M = 1 + (int(f_rest.size(1)) if f_rest is not None and f_rest.numel() else 0)
+        o = dict(dtype=torch.float32, device=dev)
+        alloc = torch.zeros if P == 0 else torch.empty
+        outputs = outputs or {}
+
+        def out(name, shape):
+            v = outputs.get(name)
+            if v is not None and v.numel() == int(torch.Size(shape).numel()) and v.is_contiguous() and v.data_ptr() % 16 == 0:
+                return v.view(shape)
+            if accumulate:
+                raise RuntimeError("accumulate=True needs preallocated outputs")
+            return alloc(shape, **o)
+        with torch.cuda.device(dev):
+            g2d = alloc((P, 3), **o)
+            g_xyz, g_dc, g_rest = out("xyz", (P, 3)), out("f_dc", (P, 1, 3)), out("f_rest", (P, M - 1, 3))
+            g_op, g_sc, g_rot = out("opacity", (P, 1)), out("scaling", (P, 3)), out("rotation", (P, 4))
+            if P != 0:
+                t = [_prep(x, n) for x, n in ((background, "background"), (xyz, "xyz"), (f_dc, "f_dc"),
+                                              (f_rest, "f_rest"), (opacity_raw, "opacity"), (scaling_raw, "scaling"),
+                                              (rotation_raw, "rotation"), (alphas, "alphas"), (viewmatrix, "viewmatrix"),
+                                              (projmatrix, "projmatrix"), (campos, "campos"),
+                                              (dL_dout_color, "dL_dout_color"), (dL_dout_depth, "dL_dout_depth"),
+                                              (dL_dout_alpha, "dL_dout_alpha"))]
+                bg, m3, dc, rest, opa, sca, rot, alp, vm, pm, cam, gc, gd, ga = t
+                rc = self._backward_raw(
+                    1 if accumulate else 0, P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(dc), _ptr(rest),
+                    _ptr(opa), _ptr(sca), float(scale_modifier), _ptr(rot), _ptr(alp), _ptr(vm), _ptr(pm), _ptr(cam),
+                    float(tan_fovx), float(tan_fovy), _ptr(radii.contiguous()), _ptr(geomBuffer), _ptr(binningBuffer),
+                    _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(ga), g2d.data_ptr(), g_xyz.data_ptr(), g_dc.data_ptr(),
+                    _ptr(g_rest), g_op.data_ptr(), g_sc.data_ptr(), g_rot.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+                if rc != 0:
+                    raise self._err("rasterize_raw_backward", rc)
+        return g2d, g_xyz, g_dc, g_rest, g_op, g_sc, g_rot
+
     def mark_visible(self, means3D, viewmatrix, projmatrix):
         P = int(means3D.size(0))
         dev = means3D.device
@@ -341,6 +477,9 @@ class CompiledBackend:
         self.needs_zeroed_outputs = False
         self.rasterize_gaussians = module.rasterize_gaussians
         self.mark_visible = module.mark_visible
+        if hasattr(module, "rasterize_gaussians_nosync"):
+            self.rasterize_gaussians_nosync = module.rasterize_gaussians_nosync
+            self.count_wait = module.count_wait
 
     def rasterize_gaussians_backward(self, *args):
         if self._ct.grad_sink is not None:      # gradients go straight into the DP bucket

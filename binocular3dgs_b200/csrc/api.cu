@@ -111,6 +111,44 @@ static int* pinned_word() {
     return w[dev];
 }
 
+// ---- tickets of the no-sync forward -----------------------------------------------------
+// b3gs_forward_nosync does not wait for R: it copies the device counter into a pinned slot,
+// records an event and hands the slot out as a ticket; b3gs_count_wait(ticket) blocks on that
+// event only.  A process-wide ring: a ticket stays valid for kCountSlots further no-sync
+// forwards (its generation is checked).
+constexpr int kCountSlots = 256;
+struct CountSlot {
+    cudaEvent_t ev = nullptr;
+    int* word = nullptr;        // pinned
+    int device = -1;
+    unsigned generation = 0;
+};
+static std::mutex g_slot_mu;
+static CountSlot g_slots[kCountSlots];
+static unsigned g_slot_next = 0;
+
+// returns the ticket (generation << 8 | slot) or -1
+static int acquire_count_slot(CountSlot** out) {
+    const int dev = current_device();
+    if (dev < 0) return -1;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    const unsigned idx = g_slot_next++ % kCountSlots;
+    CountSlot& s = g_slots[idx];
+    if (s.ev && s.device != dev) {   // events belong to a device
+        cudaEventDestroy(s.ev);
+        s.ev = nullptr;
+    }
+    if (!s.ev && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) { s.ev = nullptr; return -1; }
+    if (!s.word && cudaHostAlloc(reinterpret_cast<void**>(&s.word), sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) {
+        s.word = nullptr;
+        return -1;
+    }
+    s.device = dev;
+    s.generation = (s.generation + 1) & 0x3fffffu;
+    *out = &s;
+    return (int)((s.generation << 8) | idx);
+}
+
 // ---- optional per-stage device timing (bench.py roofline) ---------------------
 // When enabled, every stage is bracketed by a pair of CUDA events recorded on the
 // caller's stream; b3gs_profile_read() synchronises on them and sums the elapsed
@@ -162,14 +200,18 @@ using namespace b3;
 
 extern "C" {
 
-int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
-                 const float* background, int width, int height, const float* means3D, const float* shs,
-                 const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
-                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
-                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
-                 float* out_color, float* out_depth, float* out_alpha, int* radii, int debug, void* stream,
-                 int* num_rendered) {
+// capacity < 0: the exact path (one host wait for R).  capacity >= 0: never waits; the binning
+// blob holds `capacity` instances, *ticket receives the count ticket.
+static int forward_impl(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
+                        const float* background, int width, int height, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                        float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha,
+                        int* radii, int debug, void* stream, int* num_rendered, int capacity, int* ticket,
+                        const float* shs_rest = nullptr, int raw = 0) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool nosync = capacity >= 0;
     if (num_rendered) *num_rendered = 0;
     if (P < 0 || width <= 0 || height <= 0 || D < 0 || D > 3)
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward: bad sizes (P>=0, width,height>0, 0<=D<=3)");
@@ -217,6 +259,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
 
         PreprocessArgs pa;
         pa.P = P; pa.D = D; pa.M = M;
+        pa.raw = raw; pa.shs_rest = shs_rest;
         pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations;
         pa.opacities = opacities; pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
         pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
@@ -245,8 +288,19 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         // surface).  Start its copy now, then enqueue the P-sized half of the binning, and
         // only then wait: the GPU sorts by depth while the host sleeps on the event and
         // allocates.  (rasterizer_impl.cu:282 blocks the whole device with cudaMemcpy.)
-        int* hw = pinned_word();
-        cudaEvent_t ev = count_event();
+        int* hw = nullptr;
+        cudaEvent_t ev = nullptr;
+        if (nosync) {
+            CountSlot* slot = nullptr;
+            const int tk = acquire_count_slot(&slot);
+            if (tk < 0) return fail(B3GS_ERR_ALLOC, "b3gs_forward_nosync: count slot allocation failed");
+            hw = slot->word; ev = slot->ev;
+            *hw = -1;
+            if (ticket) *ticket = tk;
+        } else {
+            hw = pinned_word();
+            ev = count_event();
+        }
         if (!hw || !ev) return fail(B3GS_ERR_ALLOC, "b3gs_forward: pinned word / event allocation failed");
         e = cudaMemcpyAsync(hw, pa.num_rendered, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(ev, st);
@@ -266,9 +320,13 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "binning phase 1", e);
         B3_CHECK_STAGE("binning phase 1");
 
-        e = cudaEventSynchronize(ev);
-        if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "wait for num_rendered", e);
-        R = *hw;
+        if (nosync) {
+            R = capacity;   // the blob is sized by the caller's estimate; the device clamps to it
+        } else {
+            e = cudaEventSynchronize(ev);
+            if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "wait for num_rendered", e);
+            R = *hw;
+        }
     }
 
     BinLayout bl(R, P, grid_x, grid_y);
@@ -280,6 +338,7 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
     {
         BinningPhase2Args ba;
         ba.P = P; ba.R = R; ba.grid_x = grid_x; ba.grid_y = grid_y;
+        ba.count_unknown = nosync ? 1 : 0;
         ba.records = reinterpret_cast<const float4*>(geo + gl.records);
         ba.depths = reinterpret_cast<const float*>(geo + gl.depths);
         ba.radii = radii;
@@ -311,11 +370,62 @@ int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, i
         }
         B3_CHECK_STAGE("composite_forward");
     }
-    if (num_rendered) *num_rendered = R;
+    if (num_rendered) *num_rendered = nosync ? -1 : R;
     return B3GS_OK;
 }
 
-int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float* background, int width, int height,
+int b3gs_forward(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
+                 const float* background, int width, int height, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                 float* out_color, float* out_depth, float* out_alpha, int* radii, int debug, void* stream,
+                 int* num_rendered) {
+    return forward_impl(geometry, binning, image, P, D, M, background, width, height, means3D, shs, colors_precomp,
+                        opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
+                        tan_fovx, tan_fovy, prefiltered, out_color, out_depth, out_alpha, radii, debug, stream,
+                        num_rendered, -1, nullptr);
+}
+
+int b3gs_forward_nosync_supported(int P, int width, int height) {
+    return P > 0 && binning_uses_tile_bins(P, (width + B3_TILE_X - 1) / B3_TILE_X, (height + B3_TILE_Y - 1) / B3_TILE_Y) ? 1 : 0;
+}
+
+int b3gs_forward_nosync(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
+                        const float* background, int width, int height, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                        float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha,
+                        int* radii, void* stream, int capacity, int* ticket) {
+    if (capacity < 1 || !ticket) return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward_nosync: capacity >= 1 and a ticket are required");
+    if (!b3gs_forward_nosync_supported(P, width, height))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward_nosync: not supported for these sizes (use b3gs_forward)");
+    return forward_impl(geometry, binning, image, P, D, M, background, width, height, means3D, shs, colors_precomp,
+                        opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
+                        tan_fovx, tan_fovy, prefiltered, out_color, out_depth, out_alpha, radii, 0, stream, nullptr,
+                        capacity, ticket);
+}
+
+int b3gs_count_wait(int ticket, int* num_rendered) {
+    if (ticket < 0 || !num_rendered) return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_count_wait: bad ticket");
+    cudaEvent_t ev;
+    int* word;
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        const CountSlot& s = g_slots[ticket & 0xff];
+        if (!s.ev || s.generation != ((unsigned)ticket >> 8))
+            return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_count_wait: the ticket has expired (more than 256 later forwards)");
+        ev = s.ev; word = s.word;
+    }
+    cudaError_t e = cudaEventSynchronize(ev);
+    if (e != cudaSuccess) return fail(B3GS_ERR_CUDA, "b3gs_count_wait", e);
+    *num_rendered = *word;
+    return B3GS_OK;
+}
+
+static int backward_impl(unsigned flags, int raw, const float* shs_rest, const float* opacities_raw, float* dL_dsh_rest,
+                         int P, int D, int M, int R, const float* background, int width, int height,
                   const float* means3D, const float* shs, const float* colors_precomp, const float* alphas,
                   const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
                   const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
@@ -331,9 +441,12 @@ int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float*
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null state buffer");
     if (!dL_dpix || !alphas || !radii || !means3D || !background)  // dL_dpix_depth / dL_dalphas: NULL == zeros
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null required input pointer");
-    if (!dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_ddepth || !dL_dmean3D || !dL_dcov3D ||
-        !dL_dscale || !dL_drot || (M > 0 && shs && !dL_dsh))
+    // dL_dconic, dL_dcolor, dL_ddepth, dL_dcov3D may be NULL: intermediates the caller does not want
+    if (!dL_dmean2D || !dL_dopacity || !dL_dmean3D || !dL_dscale || !dL_drot || (M > 0 && shs && !dL_dsh))
         return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward: null gradient output pointer");
+    if (raw && (!opacities_raw || !scales || !rotations || cov3D_precomp || colors_precomp ||
+                (M > 1 && (!shs_rest || !dL_dsh_rest))))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward_raw: raw parameters missing, or precomputed inputs given");
     const int grid_x = (width + B3_TILE_X - 1) / B3_TILE_X, grid_y = (height + B3_TILE_Y - 1) / B3_TILE_Y;
 
     GeomLayout gl(P);
@@ -373,6 +486,7 @@ int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float*
 
     PreBackwardArgs pa;
     pa.P = P; pa.D = D; pa.M = M;
+    pa.raw = raw; pa.shs_rest = shs_rest; pa.opacities = opacities_raw; pa.dL_dsh_rest = dL_dsh_rest;
     pa.means3D = means3D; pa.radii = radii; pa.shs = shs;
     pa.clamped = reinterpret_cast<const uint8_t*>(geo + gl.clamped);
     pa.scales = scales; pa.rotations = rotations; pa.scale_modifier = scale_modifier;
@@ -391,6 +505,56 @@ int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float*
     }
     B3_CHECK_STAGE("preprocess_backward");
     return B3GS_OK;
+}
+
+int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float* background, int width, int height,
+                        const float* means3D, const float* shs, const float* colors_precomp, const float* alphas,
+                        const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                        float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                        const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+                        float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                        float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream) {
+    return backward_impl(flags, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
+                         colors_precomp, alphas, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                         campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
+                         dL_dpix_depth, dL_dalphas, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
+                         dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream);
+}
+
+// ---- the raw-parameter entry: activations fused into K1 and K8+K9
+int b3gs_forward_raw(b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M,
+                     const float* background, int width, int height, const float* xyz, const float* f_dc,
+                     const float* f_rest, const float* opacity_raw, const float* scaling_raw, float scale_modifier,
+                     const float* rotation_raw, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                     float tan_fovx, float tan_fovy, float* out_color, float* out_depth, float* out_alpha, int* radii,
+                     void* stream, int capacity, int* num_rendered_or_ticket) {
+    if (!f_dc || !opacity_raw || !scaling_raw || !rotation_raw || M < 1 || (M > 1 && !f_rest))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward_raw: f_dc, (f_rest), opacity, scaling, rotation are required");
+    if (capacity >= 0 && !b3gs_forward_nosync_supported(P, width, height))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward_raw: capacity >= 0 (no-sync) is not supported for these sizes");
+    if (capacity >= 0 && (capacity < 1 || !num_rendered_or_ticket))
+        return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_forward_raw: capacity >= 1 and a ticket are required");
+    return forward_impl(geometry, binning, image, P, D, M, background, width, height, xyz, f_dc, nullptr, opacity_raw,
+                        scaling_raw, scale_modifier, rotation_raw, nullptr, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                        tan_fovy, 0, out_color, out_depth, out_alpha, radii, 0, stream,
+                        capacity < 0 ? num_rendered_or_ticket : nullptr, capacity,
+                        capacity < 0 ? nullptr : num_rendered_or_ticket, f_rest, 1);
+}
+
+int b3gs_backward_raw(unsigned flags, int P, int D, int M, int R, const float* background, int width, int height,
+                      const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw,
+                      const float* scaling_raw, float scale_modifier, const float* rotation_raw, const float* alphas,
+                      const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
+                      float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                      const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+                      float* dL_dxyz, float* dL_df_dc, float* dL_df_rest, float* dL_dopacity_raw,
+                      float* dL_dscaling_raw, float* dL_drotation_raw, void* stream) {
+    return backward_impl(flags, 1, f_rest, opacity_raw, dL_df_rest, P, D, M, R, background, width, height, xyz, f_dc,
+                         nullptr, alphas, scaling_raw, scale_modifier, rotation_raw, nullptr, viewmatrix, projmatrix,
+                         campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
+                         dL_dpix_depth, dL_dalphas, dL_dmean2D, nullptr, dL_dopacity_raw, nullptr, nullptr, dL_dxyz,
+                         nullptr, dL_df_dc, dL_dscaling_raw, dL_drotation_raw, 0, stream);
 }
 
 int b3gs_backward(int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,

@@ -1000,7 +1000,8 @@ __global__ void __launch_bounds__(256) bin_chunk_sums(const uint32_t* __restrict
 
 // exclusive scan of the tile totals -> tile_start (in place) and ranges ((0,0) for empty tiles,
 // as the reference's memset + identifyTileRanges leave them)
-__global__ void __launch_bounds__(1024) bin_tile_scan(uint32_t* __restrict__ tile_total, int T, uint2* __restrict__ ranges) {
+__global__ void __launch_bounds__(1024) bin_tile_scan(uint32_t* __restrict__ tile_total, int T, uint2* __restrict__ ranges,
+                                                     uint32_t cap) {
     __shared__ uint32_t s_warp[32];
     uint32_t carry = 0;
     for (int base = 0; base < T; base += 1024) {
@@ -1011,7 +1012,8 @@ __global__ void __launch_bounds__(1024) bin_tile_scan(uint32_t* __restrict__ til
         if (t < T) {
             const uint32_t start = carry + inc - v;
             tile_total[t] = start;
-            ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+            // cap: only the no-sync forward can see more instances than the list holds; it drops them
+            ranges[t] = v ? make_uint2(min(start, cap), min(start + v, cap)) : make_uint2(0u, 0u);
         }
         carry += total;
     }
@@ -1089,7 +1091,7 @@ static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t s
     tile_bins_kernel<false><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
     const dim3 grid((L.T + 255) / 256, L.nchunks);
     bin_chunk_sums<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
-    bin_tile_scan<<<1, 1024, 0, stream>>>(tile_total, L.T, a.ranges);
+    bin_tile_scan<<<1, 1024, 0, stream>>>(tile_total, L.T, a.ranges, k.cap);
     bin_apply<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
     tile_bins_kernel<true><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
     count_launch(5);

@@ -76,6 +76,46 @@ __device__ __forceinline__ float gauss_power(float dx, float dy, float cx, float
     return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cy)));
 }
 
+// ---- the reference's parameter activations (scene/gaussian_model.py:27-40, :95-115) ------
+// One definition for the stand-alone activation kernels (parameters.cu) and for the raw-
+// parameter entry that fuses them into the preprocess and its backward: explicit rounding, so
+// the fused and the unfused path are bit-identical whatever the surrounding code is.
+__device__ __forceinline__ float act_scale(float raw) { return expf(raw); }                       // torch.exp
+__device__ __forceinline__ float act_opacity(float raw) {                                        // torch.sigmoid
+    return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-raw)));
+}
+// torch.nn.functional.normalize(q, dim=1) = q / max(||q||_2, 1e-12) as torch 2.x evaluates it on
+// CUDA for a (P,4) tensor: the reduction keeps two strided accumulators, i.e.
+// (x0^2 + x2^2) + (x1^2 + x3^2) with every square rounded first, then sqrt, then one IEEE
+// division per component.  Found by tools/activation_probe.py (0 mismatching rows of 2M against
+// torch 2.11; every other order of the four squares differs in ~15 % of the rows) — a last-bit
+// difference in a rotation is enough to flip an alpha < 1/255 test somewhere in an image.
+__device__ __forceinline__ float quat_norm(const float4& q) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.z, q.z)),
+                                __fadd_rn(__fmul_rn(q.y, q.y), __fmul_rn(q.w, q.w))));
+}
+__device__ __forceinline__ float4 act_rotation(const float4& q) {
+    const float n = fmaxf(quat_norm(q), 1e-12f);
+    return make_float4(__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n));
+}
+// duals: gradient w.r.t. the raw parameter from the gradient u w.r.t. the activated one
+__device__ __forceinline__ float act_opacity_grad(float raw, float u) {
+    const float s = act_opacity(raw);
+    return u * ((1.f - s) * s);
+}
+__device__ __forceinline__ float4 act_rotation_grad(const float4& q, const float4& u) {
+    const float norm = quat_norm(q);
+    if (norm > 1e-12f) {
+        // y = q/|q|:  dq = (u - y (y.u)) / |q|
+        const float inv = __fdiv_rn(1.f, norm);
+        const float yx = q.x * inv, yy = q.y * inv, yz = q.z * inv, yw = q.w * inv;
+        const float d = yx * u.x + yy * u.y + yz * u.z + yw * u.w;
+        return make_float4((u.x - yx * d) * inv, (u.y - yy * d) * inv, (u.z - yz * d) * inv, (u.w - yw * d) * inv);
+    }
+    // clamped branch: y = q / 1e-12, the clamp passes no gradient to the norm
+    return make_float4(u.x * 1e12f, u.y * 1e12f, u.z * 1e12f, u.w * 1e12f);
+}
+
 // ---- TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) + mbarrier, sm_90+/sm_100a -------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -9,8 +9,13 @@ namespace b3 {
 void count_launch(unsigned n = 1);
 
 // ---------------------------------------------------------------- K1 / K10
+// raw != 0 (the raw-parameter entry, b3gs_forward_raw / b3gs_backward_raw): `scales`,
+// `rotations`, `opacities` hold the reference's RAW parameters and are activated on load
+// (exp, normalize, sigmoid), `shs` is f_dc (P,1,3) and `shs_rest` is f_rest (P,M-1,3).
 struct PreprocessArgs {
     int P, D, M;
+    int raw;
+    const float* shs_rest;
     const float* means3D;
     const float* scales;
     float scale_modifier;
@@ -55,7 +60,8 @@ size_t binning_phase1_scratch_bytes(int P);
 cudaError_t run_binning_phase1(const BinningPhase1Args& a, cudaStream_t stream);
 
 struct BinningPhase2Args {
-    int P, R;
+    int P, R;                       // R: instances, or (count_unknown) the capacity of point_list
+    int count_unknown;              // != 0: the true count may exceed R; positions are clamped to it
     int grid_x, grid_y;
     const float4* records;
     const float* depths;
@@ -115,6 +121,10 @@ void set_backward_pixels(int n);  // 0 = automatic
 // ---------------------------------------------------------------- K8 + K9 fused
 struct PreBackwardArgs {
     int P, D, M;
+    int raw;                 // as PreprocessArgs::raw; gradients are then w.r.t. the raw parameters
+    const float* shs_rest;
+    const float* opacities;  // raw mode only (sigmoid'); unused otherwise
+    float* dL_dsh_rest;      // raw mode: dL_dsh is d f_dc, this is d f_rest
     const float* means3D;
     const int* radii;
     const float* shs;

@@ -39,13 +39,10 @@ __global__ void __launch_bounds__(256) activate_forward_kernel(int P, int M, con
         const unsigned g = i / row, k = i - g * row;
         shs[i] = k < 3 ? f_dc[g * 3 + k] : f_rest[g * (row - 3) + (k - 3)];
     }
-    for (unsigned i = tid; i < 3u * P; i += stride) scales[i] = expf(scaling_raw[i]);
+    for (unsigned i = tid; i < 3u * P; i += stride) scales[i] = act_scale(scaling_raw[i]);
     for (unsigned g = tid; g < (unsigned)P; g += stride) {
-        opacities[g] = __fdiv_rn(1.f, 1.f + expf(-opacity_raw[g]));
-        const float4 q = reinterpret_cast<const float4*>(rotation_raw)[g];
-        // F.normalize: v / max(||v||_2, 1e-12)
-        const float inv = __fdiv_rn(1.f, fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f));
-        reinterpret_cast<float4*>(rotations)[g] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+        opacities[g] = act_opacity(opacity_raw[g]);
+        reinterpret_cast<float4*>(rotations)[g] = act_rotation(reinterpret_cast<const float4*>(rotation_raw)[g]);
     }
 }
 
@@ -67,29 +64,12 @@ __global__ void __launch_bounds__(256) activate_backward_kernel(
         }
     }
     if (g_scales)
-        for (unsigned i = tid; i < 3u * P; i += stride) g_scaling_raw[i] = g_scales[i] * expf(scaling_raw[i]);
+        for (unsigned i = tid; i < 3u * P; i += stride) g_scaling_raw[i] = g_scales[i] * act_scale(scaling_raw[i]);
     for (unsigned g = tid; g < (unsigned)P; g += stride) {
-        if (g_opacities) {
-            const float s = __fdiv_rn(1.f, 1.f + expf(-opacity_raw[g]));
-            g_opacity_raw[g] = g_opacities[g] * ((1.f - s) * s);
-        }
-        if (g_rotations) {
-            const float4 q = reinterpret_cast<const float4*>(rotation_raw)[g];
-            const float4 u = reinterpret_cast<const float4*>(g_rotations)[g];
-            const float norm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
-            float4 o;
-            if (norm > 1e-12f) {
-                // y = q/|q|:  dq = (u - y (y.u)) / |q|
-                const float inv = __fdiv_rn(1.f, norm);
-                const float yx = q.x * inv, yy = q.y * inv, yz = q.z * inv, yw = q.w * inv;
-                const float d = yx * u.x + yy * u.y + yz * u.z + yw * u.w;
-                o = make_float4((u.x - yx * d) * inv, (u.y - yy * d) * inv, (u.z - yz * d) * inv, (u.w - yw * d) * inv);
-            } else {
-                // clamped branch: y = q / 1e-12, the clamp passes no gradient to the norm
-                o = make_float4(u.x * 1e12f, u.y * 1e12f, u.z * 1e12f, u.w * 1e12f);
-            }
-            reinterpret_cast<float4*>(g_rotation_raw)[g] = o;
-        }
+        if (g_opacities) g_opacity_raw[g] = act_opacity_grad(opacity_raw[g], g_opacities[g]);
+        if (g_rotations)
+            reinterpret_cast<float4*>(g_rotation_raw)[g] = act_rotation_grad(
+                reinterpret_cast<const float4*>(rotation_raw)[g], reinterpret_cast<const float4*>(g_rotations)[g]);
     }
 }
 

@@ -22,6 +22,8 @@ __device__ const float kSH_C1 = 0.4886025119029199f;
 
 struct PreParams {
     int P, D, M;
+    int raw;
+    const float* shs_rest;
     const float* means3D;
     const float* scales;
     float scale_modifier;
@@ -50,11 +52,14 @@ struct PreParams {
 // SH -> RGB, forward.cu:20-71.  dir components are IEEE divisions by the IEEE
 // square root of dot3(dx,dx,dy,dy,dz,dz).  Each basis coefficient is formed as a
 // scalar first and then fused into the running sum, in coefficient order.
-__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh, float x, float y, float z,
-                                          float& r, float& g, float& b) {
-    float c0 = __fmul_rn(sh[0], 0.28209479177387814f);
-    float c1 = __fmul_rn(sh[1], 0.28209479177387814f);
-    float c2 = __fmul_rn(sh[2], 0.28209479177387814f);
+// `sh0` holds coefficient 0; coefficient k >= 1 is sh[3k + c] (for the concatenated (P,M,3)
+// tensor both are the same pointer; for the raw-parameter entry sh0 = f_dc and sh = f_rest
+// shifted down by one coefficient).
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh0, const float* __restrict__ sh,
+                                          float x, float y, float z, float& r, float& g, float& b) {
+    float c0 = __fmul_rn(sh0[0], 0.28209479177387814f);
+    float c1 = __fmul_rn(sh0[1], 0.28209479177387814f);
+    float c2 = __fmul_rn(sh0[2], 0.28209479177387814f);
 #define B3_SH_ACC(coef, k)                       \
     {                                            \
         float cf_ = (coef);                      \
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
     // coalesced staging of the 12-byte-stride inputs
     for (int i = threadIdx.x; i < n * 3; i += 256) {
         s_mean[i] = p.means3D[(size_t)base * 3 + i];
-        if (p.scales) s_scale[i] = p.scales[(size_t)base * 3 + i];
+        if (p.scales) s_scale[i] = p.raw ? act_scale(p.scales[(size_t)base * 3 + i]) : p.scales[(size_t)base * 3 + i];
     }
     __syncthreads();
     const int t = threadIdx.x;
@@ -165,7 +170,8 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
             const float* c = p.cov3D_precomp + (size_t)idx * 6;
             c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+            float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+            if (p.raw) q = act_rotation(q);
             const float qr = q.x, qx = q.y, qy = q.z, qz = q.w;
             const float sx = __fmul_rn(s_scale[3 * t], p.scale_modifier);
             const float sy = __fmul_rn(s_scale[3 * t + 1], p.scale_modifier);
@@ -249,8 +255,9 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
                     const float dx = __fsub_rn(x, camp[0]), dy = __fsub_rn(y, camp[1]), dz = __fsub_rn(z, camp[2]);
                     const float len = __fsqrt_rn(dot3(dx, dx, dy, dy, dz, dz));
                     float sr, sg, sb;
-                    sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, __fdiv_rn(dx, len), __fdiv_rn(dy, len),
-                              __fdiv_rn(dz, len), sr, sg, sb);
+                    const float* sh0 = p.raw ? p.shs + (size_t)idx * 3 : p.shs + (size_t)idx * p.M * 3;
+                    const float* shk = p.raw ? p.shs_rest + (size_t)idx * (p.M - 1) * 3 - 3 : sh0;
+                    sh_to_rgb(p.D, sh0, shk, __fdiv_rn(dx, len), __fdiv_rn(dy, len), __fdiv_rn(dz, len), sr, sg, sb);
                     sr = __fadd_rn(sr, 0.5f); sg = __fadd_rn(sg, 0.5f); sb = __fadd_rn(sb, 0.5f);
                     if (sr < 0.0f) { clamp_bits |= 1; sr = 0.0f; }
                     if (sg < 0.0f) { clamp_bits |= 2; sg = 0.0f; }
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(256, 6) preprocess_kernel(PreParams p) {
                     const float* c = p.colors_precomp + (size_t)idx * 3;
                     cr = c[0]; cg = c[1]; cbl = c[2];
                 }
-                const float op = p.opacities[idx];
+                const float op = p.raw ? act_opacity(p.opacities[idx]) : p.opacities[idx];
                 const float tau = cull_threshold(pix_x, pix_y, conx, cony, conz, op);
                 depth = pz;
                 radius_out = ri;
@@ -317,6 +324,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream) {
     PreParams p;
     p.P = a.P; p.D = a.D; p.M = a.M;
+    p.raw = a.raw; p.shs_rest = a.shs_rest;
     p.means3D = a.means3D; p.scales = a.scales; p.scale_modifier = a.scale_modifier;
     p.rotations = a.rotations; p.opacities = a.opacities; p.shs = a.shs;
     p.cov3D_precomp = a.cov3D_precomp; p.colors_precomp = a.colors_precomp;

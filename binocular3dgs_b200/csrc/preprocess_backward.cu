@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
     const bool visible = p.radii[idx] > 0;
     const bool acc = p.accumulate != 0;
     const int ncoef = (p.D + 1) * (p.D + 1);
-    float* dsh = p.dL_dsh ? p.dL_dsh + i * p.M * 3 : nullptr;
+    // coefficient 0 goes to dsh0[0..2], coefficient k >= 1 to dshk[3k..3k+2]: one tensor (P,M,3), or —
+    // raw-parameter entry — d f_dc (P,1,3) and d f_rest (P,M-1,3) shifted down by one coefficient
+    float* dsh0 = p.dL_dsh ? (p.raw ? p.dL_dsh + i * 3 : p.dL_dsh + i * p.M * 3) : nullptr;
+    float* dshk = p.dL_dsh ? (p.raw ? p.dL_dsh_rest + i * (p.M - 1) * 3 - 3 : dsh0) : nullptr;
+    float4 q_raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float scale_act[3] = {1.f, 1.f, 1.f};   // d scale / d raw scale
 
     if (visible) {
         const float4* gp = reinterpret_cast<const float4*>(p.grads + i * B3_GRAD_STRIDE);
@@ -93,10 +98,17 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
 #pragma unroll
             for (int k = 0; k < 6; k++) c3d[k] = p.cov3D_precomp[6 * i + k];
         } else {
-            sx = p.scale_modifier * p.scales[3 * i];
-            sy = p.scale_modifier * p.scales[3 * i + 1];
-            sz = p.scale_modifier * p.scales[3 * i + 2];
+            float s0 = p.scales[3 * i], s1 = p.scales[3 * i + 1], s2 = p.scales[3 * i + 2];
             q = reinterpret_cast<const float4*>(p.rotations)[idx];
+            if (p.raw) {
+                s0 = act_scale(s0); s1 = act_scale(s1); s2 = act_scale(s2);
+                scale_act[0] = s0; scale_act[1] = s1; scale_act[2] = s2;
+                q_raw = q;
+                q = act_rotation(q);
+            }
+            sx = p.scale_modifier * s0;
+            sy = p.scale_modifier * s1;
+            sz = p.scale_modifier * s2;
             cov3d_from_scale_rot(sx, sy, sz, q, R, M, c3d);
         }
 
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
 
         // ---- SH backward (backward.cu:20-139)
         if (p.shs) {
-            const float* sh = p.shs + i * p.M * 3;
+            const float* sh = p.raw ? p.shs_rest + i * (p.M - 1) * 3 - 3 : p.shs + i * p.M * 3;  // only k >= 1 is read
             const float dox = mx - p.campos[0], doy = my - p.campos[1], doz = mz - p.campos[2];
             const float len = sqrtf(dox * dox + doy * doy + doz * doz);
             const float x = dox / len, y = doy / len, z = doz / len;
@@ -199,14 +211,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
 #define DSH(k, coef)                                             \
     {                                                            \
         const float cf_ = (coef);                                \
+        float* d_ = ((k) == 0 ? dsh0 : dshk) + 3 * (k);          \
         if (acc) {                                               \
-            dsh[3 * (k) + 0] += cf_ * dRGB[0];                   \
-            dsh[3 * (k) + 1] += cf_ * dRGB[1];                   \
-            dsh[3 * (k) + 2] += cf_ * dRGB[2];                   \
+            d_[0] += cf_ * dRGB[0];                              \
+            d_[1] += cf_ * dRGB[1];                              \
+            d_[2] += cf_ * dRGB[2];                              \
         } else {                                                 \
-            dsh[3 * (k) + 0] = cf_ * dRGB[0];                    \
-            dsh[3 * (k) + 1] = cf_ * dRGB[1];                    \
-            dsh[3 * (k) + 2] = cf_ * dRGB[2];                    \
+            d_[0] = cf_ * dRGB[0];                               \
+            d_[1] = cf_ * dRGB[1];                               \
+            d_[2] = cf_ * dRGB[2];                               \
         }                                                        \
     }
             const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
 #undef SHV
 #undef DSH
             for (int k = ncoef; k < p.M && !acc; k++) {
-                dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f;
+                dshk[3 * k] = 0.f; dshk[3 * k + 1] = 0.f; dshk[3 * k + 2] = 0.f;
             }
             const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
             const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
@@ -315,21 +328,34 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
             // dL/dscale as written is w.r.t. the UNSCALED parameter only through s; it
             // stores dot(Rt, dMt) without the modifier (backward.cu:322-325) — kept.
         }
-    } else if (dsh && !acc) {
-        for (int k = 0; k < p.M * 3; k++) dsh[k] = 0.f;
+    } else if (dsh0 && !acc) {
+        dsh0[0] = 0.f; dsh0[1] = 0.f; dsh0[2] = 0.f;
+        for (int k = 3; k < p.M * 3; k++) dshk[k] = 0.f;
     }
 
     // ---- write every output element
     p.dL_dmean2D[3 * i] = g[B3_G_MEAN2D_X];
     p.dL_dmean2D[3 * i + 1] = g[B3_G_MEAN2D_Y];
     p.dL_dmean2D[3 * i + 2] = 0.f;
-    reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(g[B3_G_CONIC_X], g[B3_G_CONIC_Y], 0.f, g[B3_G_CONIC_W]);
-    p.dL_dcolor[3 * i] = g[B3_G_COLOR_R];
-    p.dL_dcolor[3 * i + 1] = g[B3_G_COLOR_G];
-    p.dL_dcolor[3 * i + 2] = g[B3_G_COLOR_B];
-    p.dL_ddepth[idx] = g[B3_G_DEPTH];
+    // intermediates a caller may not want (NULL): the reference materialises all of them
+    if (p.dL_dconic)
+        reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(g[B3_G_CONIC_X], g[B3_G_CONIC_Y], 0.f, g[B3_G_CONIC_W]);
+    if (p.dL_dcolor) {
+        p.dL_dcolor[3 * i] = g[B3_G_COLOR_R];
+        p.dL_dcolor[3 * i + 1] = g[B3_G_COLOR_G];
+        p.dL_dcolor[3 * i + 2] = g[B3_G_COLOR_B];
+    }
+    if (p.dL_ddepth) p.dL_ddepth[idx] = g[B3_G_DEPTH];
+    if (p.dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+        for (int k = 0; k < 6; k++) p.dL_dcov3D[6 * i + k] = dcov[k];
+    }
+    if (p.raw && visible) {
+        // chain rule through the activations: the outputs are gradients of the RAW parameters
+        g[B3_G_OPACITY] = act_opacity_grad(p.opacities[idx], g[B3_G_OPACITY]);
+        dscale[0] *= scale_act[0]; dscale[1] *= scale_act[1]; dscale[2] *= scale_act[2];
+        drot = act_rotation_grad(q_raw, drot);
+    }
     // The five parameter gradients: overwritten, or — B3GS_BWD_ACCUMULATE, the second view of a
     // step writing into the same exchange bucket — added to what the earlier view left there
     // (dL_dsh was accumulated where it was formed, above).

@@ -45,13 +45,14 @@ const float* fptr(const torch::Tensor& t, const char* name, torch::Tensor& keep)
     throw std::runtime_error(std::string("b3gs.") + what + " failed (" + std::to_string(rc) + "): " + b3gs_last_error());
 }
 
+// capacity < 0: b3gs_forward (exact, one host wait); >= 0: b3gs_forward_nosync, first element = ticket
 std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
-rasterize_gaussians(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
-                    const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
-                    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
-                    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
-                    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
-                    const bool prefiltered, const bool debug) {
+forward_common(const int capacity, const torch::Tensor& background, const torch::Tensor& means3D,
+               const torch::Tensor& colors, const torch::Tensor& opacity, const torch::Tensor& scales,
+               const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+               const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+               const float tan_fovy, const int image_height, const int image_width, const torch::Tensor& sh,
+               const int degree, const torch::Tensor& campos, const bool prefiltered, const bool debug) {
     if (means3D.ndimension() != 2 || means3D.size(1) != 3) AT_ERROR("means3D must have dimensions (num_points, 3)");
     TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (no CPU path exists)");
     const int P = (int)means3D.size(0), H = image_height, W = image_width;
@@ -65,17 +66,60 @@ rasterize_gaussians(const torch::Tensor& background, const torch::Tensor& means3
     const int M = (sh.dim() >= 2 && sh.size(0) != 0) ? (int)sh.size(1) : 0;
     torch::Tensor k[11];
     int rendered = 0;
-    const int rc = b3gs_forward(
-        b3gs_buffer{resize_cb, &geom}, b3gs_buffer{resize_cb, &binning}, b3gs_buffer{resize_cb, &img}, P, degree, M,
-        fptr(background, "background", k[0]), W, H, fptr(means3D, "means3D", k[1]), fptr(sh, "sh", k[2]),
-        fptr(colors, "colors_precomp", k[3]), fptr(opacity, "opacities", k[4]), fptr(scales, "scales", k[5]),
-        scale_modifier, fptr(rotations, "rotations", k[6]), fptr(cov3D_precomp, "cov3D_precomp", k[7]),
-        fptr(viewmatrix, "viewmatrix", k[8]), fptr(projmatrix, "projmatrix", k[9]), fptr(campos, "campos", k[10]),
-        tan_fovx, tan_fovy, prefiltered ? 1 : 0, out_color.data_ptr<float>(), out_depth.data_ptr<float>(),
-        out_alpha.data_ptr<float>(), P ? radii.data_ptr<int>() : nullptr, debug ? 1 : 0,
-        at::cuda::getCurrentCUDAStream().stream(), &rendered);
+    const float *p_bg = fptr(background, "background", k[0]), *p_m3 = fptr(means3D, "means3D", k[1]),
+                *p_sh = fptr(sh, "sh", k[2]), *p_col = fptr(colors, "colors_precomp", k[3]),
+                *p_op = fptr(opacity, "opacities", k[4]), *p_sc = fptr(scales, "scales", k[5]),
+                *p_rot = fptr(rotations, "rotations", k[6]), *p_cov = fptr(cov3D_precomp, "cov3D_precomp", k[7]),
+                *p_vm = fptr(viewmatrix, "viewmatrix", k[8]), *p_pm = fptr(projmatrix, "projmatrix", k[9]),
+                *p_cam = fptr(campos, "campos", k[10]);
+    const b3gs_buffer bg_{resize_cb, &geom}, bb_{resize_cb, &binning}, bi_{resize_cb, &img};
+    void* stream = at::cuda::getCurrentCUDAStream().stream();
+    const int rc =
+        capacity < 0
+            ? b3gs_forward(bg_, bb_, bi_, P, degree, M, p_bg, W, H, p_m3, p_sh, p_col, p_op, p_sc, scale_modifier, p_rot,
+                           p_cov, p_vm, p_pm, p_cam, tan_fovx, tan_fovy, prefiltered ? 1 : 0, out_color.data_ptr<float>(),
+                           out_depth.data_ptr<float>(), out_alpha.data_ptr<float>(), P ? radii.data_ptr<int>() : nullptr,
+                           debug ? 1 : 0, stream, &rendered)
+            : b3gs_forward_nosync(bg_, bb_, bi_, P, degree, M, p_bg, W, H, p_m3, p_sh, p_col, p_op, p_sc, scale_modifier,
+                                  p_rot, p_cov, p_vm, p_pm, p_cam, tan_fovx, tan_fovy, prefiltered ? 1 : 0,
+                                  out_color.data_ptr<float>(), out_depth.data_ptr<float>(), out_alpha.data_ptr<float>(),
+                                  P ? radii.data_ptr<int>() : nullptr, stream, capacity, &rendered);
     if (rc != 0) fail("rasterize_gaussians", rc);
     return std::make_tuple(rendered, out_color, out_depth, out_alpha, radii, geom, binning, img);
+}
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rasterize_gaussians(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                    const torch::Tensor& opacity, const torch::Tensor& scales, const torch::Tensor& rotations,
+                    const float scale_modifier, const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                    const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy, const int image_height,
+                    const int image_width, const torch::Tensor& sh, const int degree, const torch::Tensor& campos,
+                    const bool prefiltered, const bool debug) {
+    return forward_common(-1, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                          viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                          prefiltered, debug);
+}
+
+// first element of the result: the ticket for count_wait (include/b3gs.h: b3gs_forward_nosync)
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rasterize_gaussians_nosync(const int capacity, const torch::Tensor& background, const torch::Tensor& means3D,
+                           const torch::Tensor& colors, const torch::Tensor& opacity, const torch::Tensor& scales,
+                           const torch::Tensor& rotations, const float scale_modifier,
+                           const torch::Tensor& cov3D_precomp, const torch::Tensor& viewmatrix,
+                           const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                           const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
+                           const torch::Tensor& campos, const bool prefiltered, const bool debug) {
+    TORCH_CHECK(capacity >= 1, "capacity must be >= 1");
+    return forward_common(capacity, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                          degree, campos, prefiltered, debug);
+}
+
+int count_wait(const int ticket) {
+    int r = 0;
+    const int rc = b3gs_count_wait(ticket, &r);
+    if (rc != 0) fail("count_wait", rc);
+    return r;
 }
 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
@@ -148,6 +192,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians", &rasterize_gaussians);
     m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward);
     m.def("mark_visible", &mark_visible);
+    m.def("rasterize_gaussians_nosync", &rasterize_gaussians_nosync);
+    m.def("count_wait", &count_wait, py::call_guard<py::gil_scoped_release>());
     m.def("launch_count", []() { return (unsigned long long)b3gs_launch_count(); });
     m.def("version", []() { return std::string(b3gs_version()); });
 }

@@ -120,6 +120,34 @@ B3GS_API int b3gs_forward(
     int* num_rendered);
 
 /*
+ * Forward WITHOUT the host synchronisation (an addition; the reference blocks the whole
+ * device at rasterizer_impl.cu:282 and b3gs_forward blocks the calling thread once).
+ * Same arguments as b3gs_forward minus `debug`, plus
+ *   capacity : how many (Gaussian, tile) instances the binning blob shall hold — the
+ *              caller's estimate, e.g. 1.5 x the largest R seen for this (P, width, height);
+ *   ticket   : HOST int, receives a ticket for b3gs_count_wait.
+ * The call only enqueues work.  R is accumulated on the device and copied to a pinned slot
+ * behind the ticket; instances beyond `capacity` are DROPPED (tile ranges are clamped to the
+ * list), so the outputs are exact iff R <= capacity.  The caller checks that with
+ * b3gs_count_wait — typically when it is about to enqueue the backward, by which time the
+ * count has long landed — and, if R > capacity, re-runs b3gs_forward (exact) before using the
+ * outputs for anything that matters.  Pass the R returned by b3gs_count_wait to b3gs_backward.
+ * b3gs_forward_nosync_supported: 1 when the direct tile binning serves these sizes (its
+ * scratch does not depend on R); otherwise use b3gs_forward.
+ * b3gs_count_wait blocks until the count behind `ticket` has landed and returns it.  A ticket
+ * expires after 256 later b3gs_forward_nosync calls of the process (error, not a hang).
+ */
+B3GS_API int b3gs_forward_nosync_supported(int P, int width, int height);
+B3GS_API int b3gs_forward_nosync(
+    b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image,
+    int P, int D, int M, const float* background, int width, int height, const float* means3D, const float* shs,
+    const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color, float* out_depth,
+    float* out_alpha, int* radii, void* stream, int capacity, int* ticket);
+B3GS_API int b3gs_count_wait(int ticket, int* num_rendered);
+
+/*
  * Backward.  Replaces CudaRasterizer::Rasterizer::backward
  * (rasterizer.h:60-89, rasterizer_impl.cu:343-447).  Argument order follows the
  * reference.  `alphas` is the forward's out_alpha.  Gradient outputs:
@@ -129,7 +157,10 @@ B3GS_API int b3gs_forward(
  *   M==0), dL_dscale float[P,3], dL_drot float[P,4].
  * Unlike the reference (rasterize_points.cu:158-167) the outputs need NOT be
  * pre-zeroed: every element is written by this call.  dL_dpix_depth and dL_dalphas may
- * be NULL (that image received no gradient: treated as zeros, and not read).
+ * be NULL (that image received no gradient: treated as zeros, and not read).  The four
+ * intermediates dL_dconic, dL_dcolor, dL_ddepth, dL_dcov3D may be NULL when the caller has no
+ * use for them (dL_dcolor is only observable with colors_precomp, dL_dcov3D with
+ * cov3D_precomp, the other two never leave rasterize_points.cu:161-162): not written then.
  */
 B3GS_API int b3gs_backward(
     int P, int D, int M, int R,
@@ -187,6 +218,40 @@ B3GS_API int b3gs_backward_flags(
     char* image_buffer, const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
     float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream);
+
+/*
+ * ---- The raw-parameter entry (an addition) --------------------
+ * The reference evaluates exp / sigmoid / normalize / cat on the raw parameters before every
+ * render (scene/gaussian_model.py:95-115, called from gaussian_renderer/__init__.py:54-83)
+ * and autograd runs their duals after every backward: ten elementwise kernels and
+ * 2 x (11 + 3M) floats per Gaussian of extra traffic each way.  These two entry points take
+ * the RAW parameters and fuse the activations into the preprocess and its backward:
+ *   xyz float[P,3]; f_dc float[P,1,3]; f_rest float[P,M-1,3] (NULL when M == 1);
+ *   opacity_raw float[P]; scaling_raw float[P,3]; rotation_raw float[P,4]
+ *   means3D = xyz, shs = cat(f_dc, f_rest), opacities = sigmoid(opacity_raw),
+ *   scales = exp(scaling_raw), rotations = rotation_raw / max(|rotation_raw|, 1e-12).
+ * Results are bit-identical to b3gs_activate_forward followed by b3gs_forward (the same
+ * device functions), and the gradients are those of the raw parameters.
+ * b3gs_forward_raw: capacity < 0 -> exact path, *num_rendered_or_ticket receives R;
+ *   capacity >= 1 -> no host wait (see b3gs_forward_nosync), it receives the ticket.
+ * b3gs_backward_raw: flags as b3gs_backward_flags (B3GS_BWD_ACCUMULATE applies to dL_dxyz,
+ *   dL_df_dc, dL_df_rest, dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw).  The
+ *   intermediates (dL_dconic, dL_dcolor, dL_ddepth, dL_dcov3D) are not materialised.
+ */
+B3GS_API int b3gs_forward_raw(
+    b3gs_buffer geometry, b3gs_buffer binning, b3gs_buffer image, int P, int D, int M, const float* background,
+    int width, int height, const float* xyz, const float* f_dc, const float* f_rest, const float* opacity_raw,
+    const float* scaling_raw, float scale_modifier, const float* rotation_raw, const float* viewmatrix,
+    const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy, float* out_color,
+    float* out_depth, float* out_alpha, int* radii, void* stream, int capacity, int* num_rendered_or_ticket);
+B3GS_API int b3gs_backward_raw(
+    unsigned flags, int P, int D, int M, int R, const float* background, int width, int height, const float* xyz,
+    const float* f_dc, const float* f_rest, const float* opacity_raw, const float* scaling_raw, float scale_modifier,
+    const float* rotation_raw, const float* alphas, const float* viewmatrix, const float* projmatrix,
+    const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+    char* image_buffer, const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+    float* dL_dxyz, float* dL_df_dc, float* dL_df_rest, float* dL_dopacity_raw, float* dL_dscaling_raw,
+    float* dL_drotation_raw, void* stream);
 
 /* Visibility mask.  Replaces Rasterizer::markVisible (rasterizer.h:24-29,
  * rasterizer_impl.cu:54-66,141-153): present[i] = (z_view > 0.2). `present` is

@@ -476,3 +476,86 @@ def test_misaligned_views_and_odd_bucket_are_safe():
     torch.cuda.synchronize()
     assert util.rel_err(bucket.views()["rotations"], ref["g_rotations"]) <= 2e-5
     assert util.rel_err(bucket.views()["shs"], ref["g_shs"]) <= 2e-5
+
+
+# ------------------------------------------------------------------ the forward without its host wait
+def _run_surface(S, scene, cam, bg, grads, cam2=None):
+    leaves = [t.detach().clone().requires_grad_(True) for t in scene.tensors()]
+    m3, sc, ro, op, sh = leaves
+    outs = []
+    for c in (cam,) if cam2 is None else (cam, cam2):      # both forwards are in flight before the backward
+        m2 = torch.zeros_like(m3, requires_grad=True)
+        outs.append(S.GaussianRasterizer(util.settings_for(c, bg, scene.sh_degree))(
+            means3D=m3, means2D=m2, opacities=op, shs=sh, scales=sc, rotations=ro))
+    gc, gd, ga = grads
+    color, radii, depth, alpha = outs[0]
+    loss = (color * gc).sum() + (depth * gd).sum() + (alpha * ga).sum()
+    if cam2 is not None:
+        loss = loss + (outs[1][0] * gc).sum()
+    loss.backward()
+    res = dict(color=color.detach(), depth=depth.detach(), alpha=alpha.detach(), radii=radii)
+    res.update({"g%d" % i: t.grad for i, t in enumerate(leaves)})
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", ["compiled", "ctypes"])
+def test_nosync_forward_equals_exact_forward_and_recovers_from_overflow(host):
+    """b3gs_forward_nosync (include/b3gs.h): after the first (exact) forward of a size, training
+    forwards do not wait for R.  Same images bit for bit, same gradients up to the order of the
+    float REDs; an undersized buffer is detected when the backward resolves the ticket, the
+    forward is redone exactly into the same output tensors, and a warning says so."""
+    from binocular3dgs_b200 import _backend
+    from binocular3dgs_b200.rasterizer import make_surface
+    back = _backend.preferred() if host == "compiled" else _backend.native()
+    if host == "compiled" and not isinstance(back, _backend.CompiledBackend):
+        pytest.skip("compiled host side not built")
+    dev = torch.device("cuda:0")
+    W, H, P = 333, 190, 20000
+    scene, cam = make_scene(P, seed=51).to(dev), make_camera(W, H).to(dev)
+    cam2 = make_camera(W, H, shift_x=0.2).to(dev)
+    bg = torch.tensor([0.2, 0.1, 0.3], device=dev)
+    grads = tuple(g.to(dev) for g in make_pixel_grads(W, H, 52))
+    S = make_surface(back)
+    pol = S.async_policy
+    assert pol is not None and pol.enabled
+    exact = _run_surface(S, scene, cam, bg, grads)                       # first call of this size: exact path
+    key = (0, P, W, H)
+    R = pol.hwm[key]
+    assert R > 0 and pol.capacity(key) >= R
+    launched = back.launch_count()
+    lazy = _run_surface(S, scene, cam, bg, grads)                        # second call: no host wait
+    assert back.launch_count() > launched and pol.overflows == 0
+    for k in ("color", "depth", "alpha", "radii"):
+        assert torch.equal(lazy[k], exact[k]), k
+    for i in range(5):
+        assert util.rel_err(lazy["g%d" % i], exact["g%d" % i]) <= 2e-5, i
+    # the binocular pair: two tickets outstanding
+    pair_exact = None
+    try:
+        pol.enabled = False
+        pair_exact = _run_surface(S, scene, cam, bg, grads, cam2)
+    finally:
+        pol.enabled = True
+    pair_lazy = _run_surface(S, scene, cam, bg, grads, cam2)
+    assert torch.equal(pair_lazy["color"], pair_exact["color"])
+    for i in range(5):
+        assert util.rel_err(pair_lazy["g%d" % i], pair_exact["g%d" % i]) <= 2e-5, i
+    # overflow: a buffer half the size it needs
+    pol.forced_capacity = max(1, R // 2)
+    try:
+        with pytest.warns(RuntimeWarning, match="re-rendering exactly"):
+            over = _run_surface(S, scene, cam, bg, grads)
+    finally:
+        pol.forced_capacity = None
+    assert pol.overflows == 1
+    for k in ("color", "depth", "alpha", "radii"):
+        assert torch.equal(over[k], exact[k]), k                          # re-rendered into the same tensors
+    for i in range(5):
+        assert util.rel_err(over["g%d" % i], exact["g%d" % i]) <= 2e-5, i
+    # without gradients (evaluation) the forward stays exact: no ticket, nothing to resolve
+    with torch.no_grad():
+        c = S.GaussianRasterizer(util.settings_for(cam, bg, scene.sh_degree))(
+            means3D=scene.means3D, means2D=torch.zeros_like(scene.means3D), opacities=scene.opacities,
+            shs=scene.shs, scales=scene.scales, rotations=scene.rotations)[0]
+    assert torch.equal(c, exact["color"])
