@@ -331,20 +331,28 @@ def dp_selfcheck(arm, dev, rank, world):
         dist.all_reduce(t)
         gathered[k] = t / world
     C.grad_sink = bucket
+    worst, identical, keep = 0.0, True, getattr(bucket, "overlap", False)
     try:
-        bucket.begin_step()
-        o = raw_forward(C, wl, cam)
-        raw_backward(C, wl, cam, o, wl.gd, wl.ga)
-        bucket.all_reduce(average=True)
+        # backward then one fused exchange, and (symmetric-memory bucket) the chunk-pipelined
+        # b3gs_backward_exchange: both must give the gathered mean, replicas bit-identical
+        for overlap in ((False, True) if hasattr(bucket, "overlap") else (False,)):
+            if hasattr(bucket, "overlap"):
+                bucket.overlap = overlap
+            bucket.begin_step()
+            o = raw_forward(C, wl, cam)
+            raw_backward(C, wl, cam, o, wl.gd, wl.ga)
+            bucket.all_reduce(average=True)
+            torch.cuda.synchronize()
+            for k, v in gathered.items():
+                d = float((bucket.views()[k].reshape(v.shape) - v).abs().max() / v.abs().max().clamp_min(1e-30))
+                worst = max(worst, d)
+            identical = identical and bool(dp.replicas_identical([bucket.flat]))
     finally:
         C.grad_sink = None
-    torch.cuda.synchronize()
-    worst = 0.0
-    for k, v in gathered.items():
-        d = float((bucket.views()[k].reshape(v.shape) - v).abs().max() / v.abs().max().clamp_min(1e-30))
-        worst = max(worst, d)
+        if hasattr(bucket, "overlap"):
+            bucket.overlap = keep
     out["sink_exchange_vs_gathered_max_rel"] = worst
-    out["replicas_identical_gradients"] = bool(dp.replicas_identical([bucket.flat]))
+    out["replicas_identical_gradients"] = identical
     # (d) densification in lockstep
     dp.seed_lockstep(777)
     xyz, scaling = scene.means3D.clone(), torch.log(scene.scales)
@@ -406,7 +414,9 @@ def main():
         if not use_dp:
             return None, None
         from binocular3dgs_b200.dp import make_bucket
-        return make_bucket(w.P, w.M, dev, prefer_peer=os.environ.get("B3GS_DP", "peer") != "nccl")
+        b, kind = make_bucket(w.P, w.M, dev, prefer_peer=os.environ.get("B3GS_DP", "peer") != "nccl")
+        b.backwards_per_step = w.views_per_step      # the last backward of a step carries the exchange
+        return b, kind
 
     def barrier():
         if world > 1:
@@ -699,6 +709,13 @@ def main():
 
     # ---------------- §8(f) rows next to the rasterizer
     next_rows = None
+    if rank == 0 and world == 1 and not args.no_extra and args.impl == "reference":
+        # the reference's training iteration from the reference's own files on the stock operator
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            next_rows = {"train_iteration": {"reference": __import__("bench_train_iteration").measure(dev, "reference")}}
+        except Exception as ex:
+            next_rows = {"train_iteration": {"error": repr(ex)}}
     if rank == 0 and world == 1 and not args.no_extra and args.impl in ("native", "veneer"):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         next_rows = {}
@@ -715,7 +732,10 @@ def main():
             row("binocular_loss", lambda: __import__("bench_loss").measure_binocular(dev))
             row("parameter_plumbing", lambda: __import__("bench_params").measure(dev, 200_000, 4))
             row("dist_cuda2", lambda: __import__("bench_knn").measure(1_000_000, "clustered", 3, which="native"))
-            row("train_iteration", lambda: __import__("bench_iteration").measure(dev, "fern", 20, 5, which=("native",)))
+            row("train_iteration", lambda: dict(
+                __import__("bench_iteration").measure(dev, "fern", 20, 5, which=("native", "native_raw")),
+                # the reference's own files (render, GaussianModel, losses, Adam) with only the rasterizer swapped
+                dropin=__import__("bench_train_iteration").measure(dev, "dropin")))
         else:
             row("dist_cuda2", lambda: __import__("bench_knn").measure(1_000_000, "clustered", 3, which="reference"))
             row("train_iteration",

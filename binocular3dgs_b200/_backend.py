@@ -100,6 +100,11 @@ class Backend:
         if self._backward_flags is not None:
             self._backward_flags.argtypes = [ctypes.c_uint] + _BWD_ARGTYPES
             self._backward_flags.restype = ctypes.c_int
+        # backward fused with the data-parallel exchange (ours only)
+        self._backward_exchange = getattr(self.lib, prefix + "backward_exchange", None)
+        if self._backward_exchange is not None:
+            self._backward_exchange.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_uint] + _BWD_ARGTYPES
+            self._backward_exchange.restype = ctypes.c_int
         # the no-sync forward (ours only): same arguments minus `debug` and `num_rendered`, plus capacity, ticket
         self._forward_nosync = getattr(self.lib, prefix + "forward_nosync", None)
         if self._forward_nosync is not None:
@@ -308,9 +313,13 @@ class Backend:
             dL_dsh = alloc((P, M, 3), **o)
             dL_dscales = alloc((P, 3), **o)
             dL_drotations = alloc((P, 4), **o)
-            sink, accumulate = self.grad_sink, False
+            sink, accumulate, exchange = self.grad_sink, False, None
             if sink is not None and hasattr(sink, "acquire"):
-                sink, accumulate = sink.acquire(self.in_autograd)
+                owner = sink
+                sink, accumulate = owner.acquire(self.in_autograd)
+                # last backward of the step on a symmetric-memory bucket: compute and exchange overlapped
+                if sink is not None and self._backward_exchange is not None and hasattr(owner, "exchange_if_last"):
+                    exchange = owner.exchange_if_last()
             if accumulate and self._backward_flags is None:
                 raise RuntimeError(f"{self.name}: this library cannot accumulate into a gradient sink")
             if sink is not None and P != 0:
@@ -338,6 +347,9 @@ class Backend:
                 rad = radii.contiguous()
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 fn = self._backward if not accumulate else (lambda *a: self._backward_flags(1, *a))
+                if exchange is not None:
+                    handle, scale = exchange
+                    fn = lambda *a: self._backward_exchange(handle, scale, 1 if accumulate else 0, *a)
                 rc = fn(
                     P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(alp), _ptr(sca),
                     float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -424,8 +425,8 @@ int b3gs_count_wait(int ticket, int* num_rendered) {
     return B3GS_OK;
 }
 
-static int backward_impl(unsigned flags, int raw, const float* shs_rest, const float* opacities_raw, float* dL_dsh_rest,
-                         int P, int D, int M, int R, const float* background, int width, int height,
+static int backward_impl(ExchangePlan* plan, float exchange_scale, unsigned flags, int raw, const float* shs_rest,
+                         const float* opacities_raw, float* dL_dsh_rest, int P, int D, int M, int R, const float* background, int width, int height,
                   const float* means3D, const float* shs, const float* colors_precomp, const float* alphas,
                   const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
                   const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx,
@@ -499,9 +500,48 @@ static int backward_impl(unsigned flags, int raw, const float* shs_rest, const f
     pa.dL_ddepth = dL_ddepth; pa.dL_dmean3D = dL_dmean3D; pa.dL_dcov3D = dL_dcov3D; pa.dL_dsh = dL_dsh;
     pa.dL_dscale = dL_dscale; pa.dL_drot = dL_drot;
     pa.accumulate = (flags & B3GS_BWD_ACCUMULATE) ? 1 : 0;
-    {
+    if (!plan) {
         StageTimer t_(ST_PREPROCESS_BWD, st);
         launch_preprocess_backward(pa, st);
+    } else {
+        // Backward + exchange, pipelined: K8+K9 runs Gaussian chunk by chunk on the caller's stream
+        // and each finished chunk's five (six) gradient ranges are all-reduced over NVLink on the
+        // plan's side stream while the next chunk is being computed.
+        StageTimer t_(ST_PREPROCESS_BWD, st);
+        float* base = exchange_base(plan);
+        struct Seg { float* ptr; int width; } segs[6] = {
+            {dL_dmean3D, 3}, {dL_dsh, raw ? 3 : 3 * M}, {raw ? dL_dsh_rest : nullptr, 3 * (M - 1)}, {dL_dopacity, 1},
+            {dL_dscale, 3}, {dL_drot, 4}};
+        for (auto& sg : segs) {
+            if (!sg.ptr || sg.width <= 0) { sg.ptr = nullptr; continue; }
+            if (sg.ptr < base || ((sg.ptr - base) & 3))
+                return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward_exchange: gradient outputs must be 16-byte aligned segments of the exchange bucket");
+        }
+        static const int forced_chunks = [] { const char* e = getenv("B3GS_DP_CHUNKS"); return e ? atoi(e) : 0; }();
+        const int chunks = forced_chunks > 0 && forced_chunks <= 16 ? forced_chunks : (P >= (1 << 19) ? 4 : (P >= (1 << 17) ? 2 : 1));
+        const int per = (((P + chunks - 1) / chunks) + 3) & ~3;
+        cudaStream_t side = exchange_stream(plan);
+        int c = 0;
+        for (int first = 0; first < P; first += per, c++) {
+            const int count = P - first < per ? P - first : per;
+            launch_preprocess_backward(pa, st, first, count);
+            cudaError_t e2 = cudaEventRecord(exchange_event(plan, c), st);
+            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(side, exchange_event(plan, c), 0);
+            ExchangeRanges rg;
+            rg.n = 0;
+            for (const auto& sg : segs) {
+                if (!sg.ptr) continue;
+                const size_t off = (size_t)(sg.ptr - base);
+                const size_t a0 = off + (size_t)first * sg.width;                       // multiple of 4: first is
+                const size_t a1 = (off + (size_t)(first + count) * sg.width + 3) & ~(size_t)3;  // segment padding is zero
+                rg.start4[rg.n] = a0 / 4; rg.len4[rg.n] = (a1 - a0) / 4; rg.n++;
+            }
+            if (e2 == cudaSuccess) e2 = exchange_chunk(plan, rg, exchange_scale, side);
+            if (e2 != cudaSuccess) return fail(B3GS_ERR_CUDA, "b3gs_backward_exchange: chunk exchange", e2);
+        }
+        cudaError_t e3 = cudaEventRecord(exchange_event(plan, 16), side);
+        if (e3 == cudaSuccess) e3 = cudaStreamWaitEvent(st, exchange_event(plan, 16), 0);
+        if (e3 != cudaSuccess) return fail(B3GS_ERR_CUDA, "b3gs_backward_exchange: join", e3);
     }
     B3_CHECK_STAGE("preprocess_backward");
     return B3GS_OK;
@@ -515,11 +555,30 @@ int b3gs_backward_flags(unsigned flags, int P, int D, int M, int R, const float*
                         const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
                         float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream) {
-    return backward_impl(flags, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
+    return backward_impl(nullptr, 1.0f, flags, 0, nullptr, nullptr, nullptr, P, D, M, R, background, width, height, means3D, shs,
                          colors_precomp, alphas, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
                          campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
                          dL_dpix_depth, dL_dalphas, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D,
                          dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream);
+}
+
+// ---- backward fused with the data-parallel exchange
+int b3gs_backward_exchange(void* exchange, float scale, unsigned flags, int P, int D, int M, int R,
+                           const float* background, int width, int height, const float* means3D, const float* shs,
+                           const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                           const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+                           const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                           const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+                           float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                           float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream) {
+    if (!exchange) return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_backward_exchange: null exchange handle");
+    return backward_impl(static_cast<ExchangePlan*>(exchange), scale, flags, 0, nullptr, nullptr, nullptr, P, D, M, R,
+                         background, width, height, means3D, shs, colors_precomp, alphas, scales, scale_modifier,
+                         rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                         binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dalphas, dL_dmean2D, dL_dconic,
+                         dL_dopacity, dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug,
+                         stream);
 }
 
 // ---- the raw-parameter entry: activations fused into K1 and K8+K9
@@ -550,7 +609,7 @@ int b3gs_backward_raw(unsigned flags, int P, int D, int M, int R, const float* b
                       const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
                       float* dL_dxyz, float* dL_df_dc, float* dL_df_rest, float* dL_dopacity_raw,
                       float* dL_dscaling_raw, float* dL_drotation_raw, void* stream) {
-    return backward_impl(flags, 1, f_rest, opacity_raw, dL_df_rest, P, D, M, R, background, width, height, xyz, f_dc,
+    return backward_impl(nullptr, 1.0f, flags, 1, f_rest, opacity_raw, dL_df_rest, P, D, M, R, background, width, height, xyz, f_dc,
                          nullptr, alphas, scaling_raw, scale_modifier, rotation_raw, nullptr, viewmatrix, projmatrix,
                          campos, tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix,
                          dL_dpix_depth, dL_dalphas, dL_dmean2D, nullptr, dL_dopacity_raw, nullptr, nullptr, dL_dxyz,

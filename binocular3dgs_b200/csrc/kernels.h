@@ -121,6 +121,7 @@ void set_backward_pixels(int n);  // 0 = automatic
 // ---------------------------------------------------------------- K8 + K9 fused
 struct PreBackwardArgs {
     int P, D, M;
+    int first, count;        // set by the launcher: the Gaussian range of this launch
     int raw;                 // as PreprocessArgs::raw; gradients are then w.r.t. the raw parameters
     const float* shs_rest;
     const float* opacities;  // raw mode only (sigmoid'); unused otherwise
@@ -150,6 +151,19 @@ struct PreBackwardArgs {
     float* dL_drot;      // [P,4]
     int accumulate;      // != 0: dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale, dL_drot are added to, not overwritten
 };
-void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream);
+void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream, int first = 0, int count = -1);
+
+// ---------------------------------------------------------------- exchange (peer_reduce.cu)
+// One chunk of the data-parallel exchange: all-reduce up to six float ranges of the symmetric
+// bucket (the five gradient segments of one Gaussian range), barriers inside the kernel.
+struct ExchangeRanges {
+    int n;
+    size_t start4[6], len4[6];      // in float4 units, relative to the bucket base
+};
+struct ExchangePlan;                // opaque: peers, flags, epoch, side stream, events
+cudaError_t exchange_chunk(ExchangePlan* plan, const ExchangeRanges& r, float scale, cudaStream_t stream);
+cudaStream_t exchange_stream(ExchangePlan* plan);
+cudaEvent_t exchange_event(ExchangePlan* plan, int i);
+float* exchange_base(ExchangePlan* plan);
 
 }  // namespace b3

@@ -56,8 +56,8 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
 // 3 blocks/SM at 80 registers; 4 / 5 / 6 spill more and are slower (B200, lego:
 // 27.4 / 29.9 / 37.6 / 41.7 us) although 6 would fit the grid into one wave.
 __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackwardArgs p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+    const int idx = p.first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.first + p.count) return;
     const size_t i = (size_t)idx;
 
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -382,8 +382,13 @@ __global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackward
     }
 }
 
-void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream) {
-    preprocess_backward_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
+// Gaussians [first, first + count) (count < 0: all P)
+void launch_preprocess_backward(const PreBackwardArgs& a0, cudaStream_t stream, int first, int count) {
+    PreBackwardArgs a = a0;
+    a.first = first;
+    a.count = count < 0 ? a.P - first : count;
+    if (a.count <= 0) return;
+    preprocess_backward_kernel<<<(a.count + 255) / 256, 256, 0, stream>>>(a);
     count_launch();
 }
 

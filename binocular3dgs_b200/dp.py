@@ -63,15 +63,19 @@ class GradientBucket:
 
     # ---- gradient-sink protocol (``_C.grad_sink = bucket``; _backend.Backend.rasterize_gaussians_backward)
     _fresh = True
+    _backwards = 0
+    backwards_per_step = 1      # 2 for the binocular pair (train.py:100,128): which backward is the last
 
     def begin_step(self):
         """The next backward overwrites the bucket (called by :meth:`all_reduce`)."""
         self._fresh = True
+        self._backwards = 0
 
     def acquire(self, autograd: bool):
         """-> (views or None, accumulate).  First backward of a step: the views, overwritten.
         Later ones: None under autograd (fresh tensors; autograd adds them into the adopted
         views), else the views again with kernel-side accumulation."""
+        self._backwards += 1
         if self._fresh:
             self._fresh = False
             return self._views, False
@@ -109,9 +113,11 @@ class PeerGradientBucket(GradientBucket):
     ``flat`` is allocated with ``torch.distributed._symmetric_memory`` so that every rank
     holds the device pointers of all peers' buckets over NVLink / NVSwitch.  The backward
     kernel writes into it exactly as into :class:`GradientBucket` (``Backend.grad_sink``);
-    :meth:`all_reduce` is then barrier -> ``b3gs_peer_allreduce`` (one in-place two-shot
-    kernel: each rank reduces its slice from all peers and stores the sum to all peers) ->
-    barrier, all on the current stream.  No NCCL call is on this path.  All ranks of ``group``
+    :meth:`all_reduce` is then ONE launch of ``b3gs_peer_allreduce_fused``: an in-place two-shot
+    all-reduce (each rank reduces its slice from all peers and stores the sum to all peers, through
+    the NVSwitch from 4 ranks up) with both cross-rank barriers inside the kernel (flag words behind
+    the data) and programmatic dependent launch behind the backward's last kernel, on the current
+    stream.  No NCCL call is on this path.  All ranks of ``group``
     must construct the bucket collectively.  CUDA only.
     """
 
@@ -135,9 +141,12 @@ class PeerGradientBucket(GradientBucket):
         from . import _backend
         group = dist.group.WORLD if group is None else group
         self._group = group
-        self.flat = symm_mem.empty(n, dtype=torch.float32, device=device)
-        self.flat.zero_()
-        self._handle = symm_mem.rendezvous(self.flat, group)
+        # 64 flag words behind the data: the in-kernel barriers of b3gs_peer_allreduce_fused
+        self._storage = symm_mem.empty(n + 64, dtype=torch.float32, device=device)
+        self._storage.zero_()
+        self.flat = self._storage[:n]
+        self._epoch = 0
+        self._handle = symm_mem.rendezvous(self._storage, group)
         self.world, self.rank = self._handle.world_size, self._handle.rank
         if self.world > 8:
             raise RuntimeError("b3gs_peer_allreduce supports up to 8 peers (one NVSwitch domain)")
@@ -161,6 +170,48 @@ class PeerGradientBucket(GradientBucket):
         self._fn_mc.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float,
                                 ctypes.c_void_p]
         self._fn_mc.restype = ctypes.c_int
+        self._fn_fused = _backend.native().lib.b3gs_peer_allreduce_fused
+        self._fn_fused.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                   ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint, ctypes.c_float, ctypes.c_void_p]
+        self._fn_fused.restype = ctypes.c_int
+        # B3GS_DP_BARRIERS=host: the two barriers as symmetric-memory signal-pad kernels around the
+        # reduction kernel (round 1's path, kept for A/B); default: inside the one fused kernel
+        self._host_barriers = os.environ.get("B3GS_DP_BARRIERS", "kernel") == "host"
+        # the exchange plan of b3gs_backward_exchange: the last backward of a step runs K8+K9 chunk by
+        # chunk and all-reduces every finished chunk while the next is computed.  OFF by default
+        # (B3GS_DP_OVERLAP=1 or bucket.overlap = True turns it on): measured on 2x B200 it LOSES —
+        # 1M Gaussians, 92 MB bucket: 1.794 ms (2 chunks) / 1.817 (4) / 1.881 (8) against 1.765 ms for
+        # backward then one fused exchange; fern pair 1.276 / 1.302 / 1.402 against 1.253 ms.  The
+        # exchange is NVLink-bound (613 GB/s per direction = 80 % of the measured 770 GB/s peer peak)
+        # and 1.7x longer than the only kernel it may legally overlap (K8+K9, 89 us); what chunking
+        # hides is less than what its extra cross-GPU barriers and the HBM contention cost.
+        lib = _backend.native().lib
+        self._plan = ctypes.c_void_p(0)
+        lib.b3gs_exchange_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        lib.b3gs_exchange_create.restype = ctypes.c_int
+        lib.b3gs_exchange_epoch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint]
+        lib.b3gs_exchange_epoch.restype = ctypes.c_uint
+        with torch.cuda.device(device):
+            rc = lib.b3gs_exchange_create(self.world, self.rank, self._ptrs, self._mc_ptr or None, n, n,
+                                          ctypes.byref(self._plan))
+        if rc != 0:
+            raise RuntimeError(f"b3gs_exchange_create failed ({rc})")
+        self._plan_epoch = lib.b3gs_exchange_epoch
+        self.overlap = os.environ.get("B3GS_DP_OVERLAP", "0") == "1" and not self._host_barriers
+        self._exchanged = False
+        self.average = True
+        torch.cuda.synchronize(device)          # flags zeroed everywhere before anyone's first epoch
+        dist.barrier(group)
+
+    def exchange_if_last(self):
+        """(plan handle, scale) when the backward that just acquired the sink is the last of the step
+        and the overlap is on: that backward is then b3gs_backward_exchange and :meth:`all_reduce`
+        has nothing left to do.  ``self.average`` decides the scale."""
+        if not self.overlap or self.world == 1 or self._backwards != self.backwards_per_step:
+            return None
+        self._exchanged = True
+        return self._plan, (1.0 / self.world) if self.average else 1.0
 
     def all_reduce(self, group=None, average: bool = True, async_op: bool = False):
         if async_op:
@@ -170,11 +221,24 @@ class PeerGradientBucket(GradientBucket):
         self.begin_step()
         if self.world == 1:
             return None
+        if self._exchanged:         # done inside the last backward (b3gs_backward_exchange)
+            self._exchanged = False
+            if average != self.average:
+                raise ValueError("the exchange fused into the backward used average=%r" % self.average)
+            return None
         dev = self.flat.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            self._handle.barrier(channel=0)        # every peer's backward has written its bucket
             scale = (1.0 / self.world) if average else 1.0
+            if not self._host_barriers:
+                epoch = self._plan_epoch(self._plan, 0, 0) + 1          # one epoch sequence for both entry points
+                self._plan_epoch(self._plan, 1, epoch)
+                rc = self._fn_fused(self.world, self.rank, self._ptrs, self._mc_ptr or None, self.flat.numel(),
+                                    self.flat.numel(), epoch, scale, stream)
+                if rc != 0:
+                    raise RuntimeError(f"b3gs_peer_allreduce_fused failed ({rc})")
+                return None
+            self._handle.barrier(channel=0)        # every peer's backward has written its bucket
             if self._mc_ptr:
                 rc = self._fn_mc(self.world, self.rank, self._mc_ptr, self.flat.numel(), scale, stream)
             else:

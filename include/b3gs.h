@@ -454,6 +454,47 @@ B3GS_API int b3gs_peer_allreduce(int world, int rank, float* const* peer_buffers
 B3GS_API int b3gs_peer_allreduce_multimem(int world, int rank, float* multicast_buffer, size_t n_floats,
                                           float scale, void* stream);
 
+/* The same exchange with both cross-rank barriers INSIDE the kernel (flag words in the symmetric
+ * buffer, system-scope release/acquire) and launched with programmatic stream serialization, so
+ * it is resident while the backward's last kernel drains: ONE launch per step, no host-issued
+ * barrier.  The buffers must extend 64 32-bit words beyond flag_off_floats (>= n_floats, a multiple
+ * of 4), zeroed when created; epoch = 1, 2, 3, ... identical on every rank and incremented per
+ * call.  multicast_buffer: NULL for plain peer loads/stores, else the multicast address (NVLS).
+ * When the call has completed on `stream`, every rank's bucket holds the reduced values and no
+ * peer reads it any more.  Bounded waits: a missing peer traps after ~4 s instead of hanging. */
+B3GS_API int b3gs_peer_allreduce_fused(int world, int rank, float* const* peer_buffers, float* multicast_buffer,
+                                       size_t n_floats, size_t flag_off_floats, unsigned epoch, float scale,
+                                       void* stream);
+
+/*
+ * Backward FUSED with the exchange: compute step and collective overlapped tile by tile.
+ * b3gs_exchange_create describes the symmetric bucket once (as b3gs_peer_allreduce_fused: peers'
+ * pointers, optional multicast address, data length, flag offset) and owns a side stream.
+ * b3gs_backward_exchange is b3gs_backward_flags whose five parameter-gradient outputs
+ * (dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale, dL_drot) MUST be 16-byte aligned segments of
+ * that bucket: the per-Gaussian backward kernel (K8+K9) runs chunk by chunk (8 chunks from 256k
+ * Gaussians) on `stream`, and as soon as a chunk is written its ranges of the five segments are
+ * all-reduced (sum * scale) over NVLink by the fused kernel on the side stream while the next
+ * chunk is being computed; `stream` joins the side stream before the call returns control of the
+ * bucket.  With B3GS_BWD_ACCUMULATE (second view of a step) the exchanged values are the sums of
+ * both views.  All ranks must make the same sequence of calls.  b3gs_exchange_epoch reads (or,
+ * with set != 0, sets) the plan's barrier epoch — needed only when b3gs_peer_allreduce_fused is
+ * also used on the same buffer: the two share the flag words and one epoch sequence.
+ */
+B3GS_API int b3gs_exchange_create(int world, int rank, float* const* peer_buffers, float* multicast_buffer,
+                                  size_t n_floats, size_t flag_off_floats, void** handle_out);
+B3GS_API void b3gs_exchange_destroy(void* handle);
+B3GS_API unsigned b3gs_exchange_epoch(void* handle, int set, unsigned value);
+B3GS_API int b3gs_backward_exchange(
+    void* exchange, float scale, unsigned flags,
+    int P, int D, int M, int R, const float* background, int width, int height, const float* means3D,
+    const float* shs, const float* colors_precomp, const float* alphas, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+    char* image_buffer, const float* dL_dpix, const float* dL_dpix_depth, const float* dL_dalphas, float* dL_dmean2D,
+    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+    float* dL_dsh, float* dL_dscale, float* dL_drot, int debug, void* stream);
+
 /* The composite backward exists in three shapes — 1, 2 or 4 pixels per lane (8x4, 8x8, 16x8
  * pixels per warp) — with identical results up to float summation order; n = 0 (default)
  * picks per call from the instances-per-Gaussian ratio, n = 1|2|4 forces one (tests, A/B

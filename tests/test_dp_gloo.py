@@ -102,7 +102,7 @@ def test_peer_all_reduce_matches_nccl_on_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
                           os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("replicas bit-identical") == 3
+    assert out.stdout.count("replicas bit-identical") == 4
 
 
 def test_make_bucket_without_cuda_is_the_plain_bucket():

@@ -15,7 +15,7 @@ timed two ways on the same GPU:
 
 An iteration = render the training view + render the shifted view (binocular pair,
 train.py:122-127) + losses + backward + densification statistics + optimizer step,
-i.e. 2 "views" of BASELINE.json's metric.  CUDA events around the whole loop,
+opacity decay, i.e. 2 "views" of BASELINE.json's metric.  CUDA events around the whole loop,
 host-side Python included (it is part of what a user waits for).
 Used by bench.py ("next_rows") and runnable on its own:  python tools/bench_iteration.py fern
 """
@@ -64,8 +64,8 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
                    "densification statistics + Adam; P=%d, %dx%d" % (config, P, W, H), "views_per_iteration": 2}
 
     def run(style):
-        if style == "native":
-            surface = make_surface(_backend.native())
+        if style in ("native", "native_raw"):
+            surface = make_surface(_backend.preferred())
             adam_cls = parameters.FusedAdam
         else:
             from oracle import refbackend
@@ -78,6 +78,17 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
 
         def render(camera, acts=None):
             screenspace = torch.zeros_like(params["xyz"], requires_grad=True)
+            if style == "native_raw":
+                # the raw-parameter entry: activations and their gradients inside the operator
+                rast = surface.GaussianRasterizer(GaussianRasterizationSettings(
+                    image_height=camera.image_height, image_width=camera.image_width, tanfovx=camera.tanfovx,
+                    tanfovy=camera.tanfovy, bg=bg, scale_modifier=1.0, viewmatrix=camera.world_view_transform,
+                    projmatrix=camera.full_proj_transform, sh_degree=1, campos=camera.camera_center,
+                    prefiltered=False, debug=False))
+                image, radii, depth, alpha = rast.forward_raw(params["xyz"], screenspace, params["f_dc"],
+                                                              params["f_rest"], params["opacity"], params["scaling"],
+                                                              params["rotation"])
+                return image, radii, depth, screenspace
             if style == "native":
                 # both views of the pair see the same parameters: activate once per iteration
                 shs, opacity, scales, rotations = acts
@@ -101,7 +112,7 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
                                            params["rotation"])
             image, radii, depth, screenspace = render(cam, acts)
             shifted_image = render(cam_shift, acts)[0]
-            if style == "native":
+            if style != "reference_style":
                 disparity_loss = binocular.binocular_consistency_loss(shifted_image, depth, gt, focal_x, trans_dist)
                 loss = losses.photometric_loss(image, gt, 0.2)
             else:
@@ -114,7 +125,13 @@ def measure(dev, config="fern", iters=20, warmup=5, which=("native", "reference_
             total = loss + disparity_loss
             total.backward()
             with torch.no_grad():
-                if style == "native":
+                # train.py:163-165 (opacity_decay defaults to True, factor 0.995)
+                if style != "reference_style":
+                    parameters.opacity_decay(params["opacity"], 0.995)
+                else:
+                    o_ = torch.sigmoid(params["opacity"]) * 0.995
+                    params["opacity"].data = torch.log(o_ / (1 - o_))
+                if style != "reference_style":
                     parameters.add_densification_stats(screenspace.grad, radii, accum, denom, max_radii)
                 else:
                     vis = radii > 0

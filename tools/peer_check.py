@@ -17,7 +17,7 @@ dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=dev)
 
-for P, M in ((1001, 4), (200_000, 4), (300_001, 16)):
+for P, M in ((1001, 4), (200_000, 4), (300_001, 16), (1_000_000, 4)):
     peer, ref = PeerGradientBucket(P, M, dev), GradientBucket(P, M, dev)
     g = torch.Generator().manual_seed(7 * rank + P)
     for name in SEGMENTS:
@@ -61,8 +61,13 @@ for P, M in ((1001, 4), (200_000, 4), (300_001, 16)):
         keep, peer._mc_ptr = peer._mc_ptr, 0
         t_plain = time_it(lambda: peer.all_reduce(average=True))
         peer._mc_ptr = keep
+    # round 1's protocol: the two barriers as host-issued signal-pad kernels around the reduction
+    peer._host_barriers = True
+    t_host = time_it(lambda: peer.all_reduce(average=True))
+    peer._host_barriers = False
     if rank == 0:
-        print("P=%d M=%d (%.1f MB) world=%d: rel diff vs NCCL %.2e, replicas bit-identical; %s %.1f us, plain peer %.1f us, "
-              "NCCL %.1f us" % (P, M, peer.nbytes / 1e6, world, worst, "multimem" if mc else "peer", t_peer * 1e3,
-                                t_plain * 1e3, t_nccl * 1e3), flush=True)
+        print("P=%d M=%d (%.1f MB) world=%d: rel diff vs NCCL %.2e, replicas bit-identical; fused kernel (%s) %.1f us, "
+              "fused plain peer %.1f us, host-issued barriers %.1f us, NCCL %.1f us"
+              % (P, M, peer.nbytes / 1e6, world, worst, "multimem" if mc else "peer", t_peer * 1e3, t_plain * 1e3,
+                 t_host * 1e3, t_nccl * 1e3), flush=True)
 dist.destroy_process_group()
