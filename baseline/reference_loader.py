@@ -79,6 +79,7 @@ def render_adapter(dgr, alias):
     # initialiser: neither is on the render path); stub what the image lacks
     # (never imported for real: this repository's top-level simple_knn/ shim would pull the product
     # package into a process that must stay free of it — the reference arm of bench.py)
+    installed = []
     for name in ("plyfile", "simple_knn", "simple_knn._C"):
         if name not in sys.modules:
             m = types.ModuleType(name)
@@ -86,6 +87,7 @@ def render_adapter(dgr, alias):
             m.distCUDA2 = lambda *a, **k: None
             m.__path__ = []
             sys.modules[name] = m
+            installed.append(name)
     if root not in sys.path:
         sys.path.insert(0, root)
     saved = sys.modules.get("diff_gaussian_rasterization")
@@ -113,6 +115,8 @@ def render_adapter(dgr, alias):
             sys.modules.pop("diff_gaussian_rasterization", None)
         else:
             sys.modules["diff_gaussian_rasterization"] = saved
+        for name in installed:      # the reference's modules have bound what they import; leave no stub behind
+            sys.modules.pop(name, None)
     assert mod.GaussianRasterizer is dgr.GaussianRasterizer
     _cache[key] = (mod, mod.GaussianModel)
     return _cache[key]

@@ -268,10 +268,13 @@ def raw_forward(C, wl, cam):
 def raw_backward(C, wl, cam, out, gd, ga):
     s, e = wl.scene, torch.empty(0)
     R, color, depth, alpha, radii, geom, binning, img = out
+    # as this library's autograd surface calls it: gradients autograd would discard (of the empty
+    # colors_precomp / cov3D_precomp placeholders) are not materialised; the reference fills them
+    kw = {"skip_unobservable": True} if getattr(C, "supports_skip_unobservable", False) else {}
     return C.rasterize_gaussians_backward(wl.bg, s.means3D, radii, e, s.scales, s.rotations, 1.0, e,
                                           cam.world_view_transform, cam.full_proj_transform, cam.tanfovx,
                                           cam.tanfovy, wl.gc, gd, ga, s.shs, s.sh_degree, cam.camera_center,
-                                          geom, R, binning, img, alpha, False)
+                                          geom, R, binning, img, alpha, False, **kw)
 
 
 def make_step(arm, wl, bucket):
@@ -599,9 +602,22 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name, {}).get(dom)
         except Exception:
             traffic = None
+        # issue-slot roofline of the FP32-issue-bound stages: warp instructions per launch (ncu
+        # smsp__inst_executed.sum of the committed capture of this workload) over what 148 SMs x 4
+        # schedulers can issue in the measured time at the SM clock seen during the run
+        try:
+            islots = json.load(open(os.path.join(ROOT, "profiles", "issue_slots.json"))).get(wl.name, {})
+        except Exception:
+            islots = {}
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        for k, v in kernels.items():
+            if k in islots:
+                v["warp_instructions"] = int(islots[k])
+                v["issue_slot_frac"] = round(islots[k] / (v["ms"] * 1e-3 * 148 * 4 * sm_hz), 4)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "I_f": I_f, "R": R,
+                    "issue_slot_frac": {k: v["issue_slot_frac"] for k, v in kernels.items() if "issue_slot_frac" in v},
                     "note": "the composite kernels are FP32-issue bound, not HBM bound (ncu: issue slots ~80% busy, "
                             "DRAM ~1%); the HBM-bound kernels are listed with their own GB/s under `kernels`; "
                             "see DESIGN.md §5"}

@@ -167,6 +167,7 @@ class Backend:
         self.in_autograd = False     # set by rasterizer._RasterizeGaussians.backward around its call
         # our C-ABI treats NULL dL/ddepth, dL/dalpha as zeros; the reference veneer does not
         self.accepts_null_grads = prefix == "b3gs_"
+        self.supports_skip_unobservable = prefix == "b3gs_"
         # One persistent C callback; `user` is the slot index (0 geom, 1 binning, 2 image).
         self._tls = threading.local()
         self._cb = _RESIZE_FN(self._resize)
@@ -289,8 +290,12 @@ class Backend:
     def rasterize_gaussians_backward(
         self, background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
         projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth, dL_dout_alpha, sh, degree, campos,
-        geomBuffer, R, binningBuffer, imageBuffer, alphas, debug,
+        geomBuffer, R, binningBuffer, imageBuffer, alphas, debug, skip_unobservable=False,
     ):
+        """``skip_unobservable`` (an addition, used by the autograd surface): do not materialise
+        dL_dcolors when colours came from SH and dL_dcov3D when covariances came from scale/rotation
+        — the reference fills both (rasterize_points.cu:160,164) although autograd discards them;
+        they are returned as None then.  dL_dconic and dL_ddepth never leave this function."""
         P = int(means3D.size(0))
         H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
         if not self.accepts_null_grads:
@@ -305,11 +310,14 @@ class Backend:
             o = dict(dtype=torch.float32, device=dev)
             dL_dmeans3D = alloc((P, 3), **o)
             dL_dmeans2D = alloc((P, 3), **o)
-            dL_dcolors = alloc((P, 3), **o)
-            dL_ddepths = alloc((P, 1), **o)
-            dL_dconic = alloc((P, 2, 2), **o)
+            own = self.prefix == "b3gs_"            # the reference veneer needs all ten, zero-filled
+            want_colors = not (own and skip_unobservable and colors.numel() == 0)
+            want_cov3D = not (own and skip_unobservable and cov3D_precomp.numel() == 0)
+            dL_dcolors = alloc((P, 3), **o) if want_colors else None
+            dL_ddepths = None if own else alloc((P, 1), **o)
+            dL_dconic = None if own else alloc((P, 2, 2), **o)
             dL_dopacity = alloc((P, 1), **o)
-            dL_dcov3D = alloc((P, 6), **o)
+            dL_dcov3D = alloc((P, 6), **o) if want_cov3D else None
             dL_dsh = alloc((P, M, 3), **o)
             dL_dscales = alloc((P, 3), **o)
             dL_drotations = alloc((P, 4), **o)
@@ -354,9 +362,9 @@ class Backend:
                     P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(shs), _ptr(col), _ptr(alp), _ptr(sca),
                     float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(cam), float(tan_fovx),
                     float(tan_fovy), _ptr(rad), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
-                    _ptr(gc), _ptr(gd), _ptr(ga), dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(),
-                    dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_ddepths.data_ptr(), dL_dmeans3D.data_ptr(),
-                    dL_dcov3D.data_ptr(), _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
+                    _ptr(gc), _ptr(gd), _ptr(ga), dL_dmeans2D.data_ptr(), _ptr(dL_dconic),
+                    dL_dopacity.data_ptr(), _ptr(dL_dcolors), _ptr(dL_ddepths), dL_dmeans3D.data_ptr(),
+                    _ptr(dL_dcov3D), _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr(),
                     int(bool(debug)), stream,
                 )
                 if rc != 0:
@@ -481,6 +489,7 @@ class CompiledBackend:
     ctypes ``Backend`` bound to the same ``libb3gs.so``."""
 
     accepts_null_grads = True
+    supports_skip_unobservable = True
 
     def __init__(self, module, ctypes_backend: Backend):
         self._m = module
@@ -493,10 +502,10 @@ class CompiledBackend:
             self.rasterize_gaussians_nosync = module.rasterize_gaussians_nosync
             self.count_wait = module.count_wait
 
-    def rasterize_gaussians_backward(self, *args):
+    def rasterize_gaussians_backward(self, *args, skip_unobservable=False):
         if self._ct.grad_sink is not None:      # gradients go straight into the DP bucket
-            return self._ct.rasterize_gaussians_backward(*args)
-        return self._m.rasterize_gaussians_backward(*args)
+            return self._ct.rasterize_gaussians_backward(*args, skip_unobservable=skip_unobservable)
+        return self._m.rasterize_gaussians_backward(*args, skip_unobservable)
 
     # state that lives on the ctypes backend must be SET there too (a plain attribute
     # assignment would land on this wrapper and be ignored by the backward)

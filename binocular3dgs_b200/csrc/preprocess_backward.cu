@@ -7,6 +7,7 @@
 // the packed accumulator written by the composite backward and WRITES every
 // output element (zeros for Gaussians with radius <= 0), so no memset of the ten
 // gradient tensors is needed (rasterize_points.cu:158-167 zero-fills them).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -55,7 +56,8 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
 
 // 3 blocks/SM at 80 registers; 4 / 5 / 6 spill more and are slower (B200, lego:
 // 27.4 / 29.9 / 37.6 / 41.7 us) although 6 would fit the grid into one wave.
-__global__ void __launch_bounds__(256, 3) preprocess_backward_kernel(PreBackwardArgs p) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) preprocess_backward_kernel(PreBackwardArgs p) {
     const int idx = p.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.first + p.count) return;
     const size_t i = (size_t)idx;
@@ -388,7 +390,9 @@ void launch_preprocess_backward(const PreBackwardArgs& a0, cudaStream_t stream, 
     a.first = first;
     a.count = count < 0 ? a.P - first : count;
     if (a.count <= 0) return;
-    preprocess_backward_kernel<<<(a.count + 255) / 256, 256, 0, stream>>>(a);
+    static const int occ = [] { const char* e = getenv("B3GS_PREBWD_OCC"); return e ? atoi(e) : 3; }();
+    if (occ == 2) preprocess_backward_kernel<2><<<(a.count + 255) / 256, 256, 0, stream>>>(a);
+    else preprocess_backward_kernel<3><<<(a.count + 255) / 256, 256, 0, stream>>>(a);
     count_launch();
 }
 

@@ -133,7 +133,7 @@ rasterize_gaussians_backward(const torch::Tensor& background, const torch::Tenso
                              const c10::optional<torch::Tensor>& dL_dout_alpha, const torch::Tensor& sh,
                              const int degree, const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
                              const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
-                             const torch::Tensor& alphas, const bool debug) {
+                             const torch::Tensor& alphas, const bool debug, const bool skip_unobservable) {
     const int P = (int)means3D.size(0);
     const int H = (int)dL_dout_color.size(1), W = (int)dL_dout_color.size(2);
     const int M = (sh.dim() >= 2 && sh.size(0) != 0) ? (int)sh.size(1) : 0;
@@ -141,10 +141,16 @@ rasterize_gaussians_backward(const torch::Tensor& background, const torch::Tenso
     auto fopt = means3D.options().dtype(torch::kFloat32);
     // the reference zero-fills all ten (rasterize_points.cu:158-167); the library writes every element
     auto alloc = [&](at::IntArrayRef s) { return P == 0 ? torch::zeros(s, fopt) : torch::empty(s, fopt); };
-    torch::Tensor dL_dmeans3D = alloc({P, 3}), dL_dmeans2D = alloc({P, 3}), dL_dcolors = alloc({P, 3}),
-                  dL_ddepths = alloc({P, 1}), dL_dconic = alloc({P, 2, 2}), dL_dopacity = alloc({P, 1}),
-                  dL_dcov3D = alloc({P, 6}), dL_dsh = alloc({P, M, 3}), dL_dscales = alloc({P, 3}),
-                  dL_drotations = alloc({P, 4});
+    // dL_dconic / dL_ddepth never leave rasterize_points.cu:161-162: not materialised.  With
+    // skip_unobservable (the autograd surface) neither are dL_dcolors on the SH path and dL_dcov3D
+    // on the scale + rotation path, whose gradients autograd discards; they come back undefined (None).
+    const bool want_colors = !(skip_unobservable && colors.numel() == 0);
+    const bool want_cov3D = !(skip_unobservable && cov3D_precomp.numel() == 0);
+    torch::Tensor dL_dmeans3D = alloc({P, 3}), dL_dmeans2D = alloc({P, 3}), dL_dopacity = alloc({P, 1}),
+                  dL_dsh = alloc({P, M, 3}), dL_dscales = alloc({P, 3}), dL_drotations = alloc({P, 4});
+    torch::Tensor dL_dcolors, dL_dcov3D;
+    if (want_colors) dL_dcolors = alloc({P, 3});
+    if (want_cov3D) dL_dcov3D = alloc({P, 6});
     if (P != 0) {
         torch::Tensor k[14];
         torch::Tensor none;
@@ -160,9 +166,9 @@ rasterize_gaussians_backward(const torch::Tensor& background, const torch::Tenso
             reinterpret_cast<char*>(imageBuffer.data_ptr()), fptr(dL_dout_color, "dL_dout_color", k[11]),
             fptr(dL_dout_depth.has_value() ? *dL_dout_depth : none, "dL_dout_depth", k[12]),
             fptr(dL_dout_alpha.has_value() ? *dL_dout_alpha : none, "dL_dout_alpha", k[13]),
-            dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(), dL_dopacity.data_ptr<float>(),
-            dL_dcolors.data_ptr<float>(), dL_ddepths.data_ptr<float>(), dL_dmeans3D.data_ptr<float>(),
-            dL_dcov3D.data_ptr<float>(), M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
+            dL_dmeans2D.data_ptr<float>(), nullptr, dL_dopacity.data_ptr<float>(),
+            want_colors ? dL_dcolors.data_ptr<float>() : nullptr, nullptr, dL_dmeans3D.data_ptr<float>(),
+            want_cov3D ? dL_dcov3D.data_ptr<float>() : nullptr, M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
             dL_drotations.data_ptr<float>(), debug ? 1 : 0, at::cuda::getCurrentCUDAStream().stream());
         if (rc != 0) fail("rasterize_gaussians_backward", rc);
     }
@@ -190,7 +196,13 @@ torch::Tensor mark_visible(const torch::Tensor& means3D, const torch::Tensor& vi
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians", &rasterize_gaussians);
-    m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward);
+    m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward, py::arg("background"), py::arg("means3D"),
+          py::arg("radii"), py::arg("colors"), py::arg("scales"), py::arg("rotations"), py::arg("scale_modifier"),
+          py::arg("cov3D_precomp"), py::arg("viewmatrix"), py::arg("projmatrix"), py::arg("tan_fovx"),
+          py::arg("tan_fovy"), py::arg("dL_dout_color"), py::arg("dL_dout_depth"), py::arg("dL_dout_alpha"),
+          py::arg("sh"), py::arg("degree"), py::arg("campos"), py::arg("geomBuffer"), py::arg("R"),
+          py::arg("binningBuffer"), py::arg("imageBuffer"), py::arg("alphas"), py::arg("debug"),
+          py::arg("skip_unobservable") = false);
     m.def("mark_visible", &mark_visible);
     m.def("rasterize_gaussians_nosync", &rasterize_gaussians_nosync);
     m.def("count_wait", &count_wait, py::call_guard<py::gil_scoped_release>());

@@ -184,17 +184,20 @@ def make_surface(_C) -> SimpleNamespace:
             tracks = hasattr(_C, "in_autograd")
             if tracks:
                 _C.in_autograd = True
+            # autograd discards the gradients of inputs that were empty placeholders: no need to
+            # materialise dL_dcolors (SH path) / dL_dcov3D (scale + rotation path)
+            kw = {"skip_unobservable": True} if getattr(_C, "supports_skip_unobservable", False) else {}
             try:
                 if s.debug:
                     cpu_args = cpu_deep_copy_tuple(args)
                     try:
-                        grads = _C.rasterize_gaussians_backward(*args)
+                        grads = _C.rasterize_gaussians_backward(*args, **kw)
                     except Exception as ex:
                         torch.save(cpu_args, "snapshot_bw.dump")
                         print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                         raise ex
                 else:
-                    grads = _C.rasterize_gaussians_backward(*args)
+                    grads = _C.rasterize_gaussians_backward(*args, **kw)
             finally:
                 if tracks:
                     _C.in_autograd = False
