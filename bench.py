@@ -770,8 +770,8 @@ def main():
             "config": {"workload": wl.label(), "P": P, "width": W, "height": H,
                        "views_per_step": wl.views_per_step,
                        "parallelism": ("view-parallel dp%d, %s of the %d-byte/Gaussian gradient bucket"
-                                       % (world, "in-place two-shot all-reduce over NVLink peer memory "
-                                          "(b3gs_peer_allreduce)" if bucket_kind == "peer" else "NCCL all-reduce",
+                                       % (world, "in-place two-shot all-reduce over NVLink peer memory, barriers inside "
+                                          "the kernel (b3gs_peer_allreduce_fused)" if bucket_kind == "peer" else "NCCL all-reduce",
                                           4 * (11 + 3 * M))) if use_dp else
                                       ("single GPU" if world == 1 else "%d independent replicas" % world),
                        "l2": "flushed between steps (512 MiB memset outside the per-step event pairs)"},
