@@ -13,6 +13,8 @@
 // launch/protocol latency.  The two barriers around it (peers' backward stores visible
 // before, reduced values landed after) are the symmetric-memory signal-pad barriers issued
 // by the host side on the same stream (dp.PeerGradientBucket).
+#include <cstdlib>
+
 #include "../../include/b3gs.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -124,7 +126,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t epoch) {
 
 constexpr int kFlagWords = 64;   // [0,8) ready, [8,16) done, [16] block counter of this rank
 
-template <int N, bool kMultimem>
+template <int N, bool kMultimem, int kU>
 __global__ void __launch_bounds__(256) peer_allreduce_fused_kernel(const __grid_constant__ PeerPtrs peers, float* mc,
                                                                   int world, int rank, size_t n4, size_t flag_off,
                                                                   uint32_t epoch, float scale) {
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_fused_kernel(const __grid_
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (kMultimem) {
-        constexpr int kUnroll = 4;
+        constexpr int kUnroll = kU;
         for (size_t base = lo + t0; base < hi; base += stride * kUnroll) {
             float4 s[kUnroll];
 #pragma unroll
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_fused_kernel(const __grid_
             }
         }
     } else {
-        constexpr int kUnroll = N <= 2 ? 4 : 2;
+        constexpr int kUnroll = N <= 2 ? kU : (kU > 2 ? kU / 2 : 1);
         for (size_t base = lo + t0; base < hi; base += stride * kUnroll) {
             float4 v[kUnroll][N];
 #pragma unroll
@@ -376,8 +378,17 @@ extern "C" int b3gs_peer_allreduce_fused(int world, int rank, float* const* peer
     for (int r = 0; r < world; r++)
         if (!pp.p[r] || (reinterpret_cast<uintptr_t>(pp.p[r]) & 15)) return -1;
     const size_t n4 = n_floats / 4;
+    // tuning knobs (read per call so that one process can sweep them): independent 16-byte
+    // requests in flight per thread, resident blocks per SM
+    const char* eu = getenv("B3GS_AR_UNROLL");
+    const char* eb = getenv("B3GS_AR_BPSM");
+    // Through the switch (multimem) FEWER requests in flight are faster — 8x B200, 92 MB bucket:
+    // 2 per thread x 2 blocks/SM 239 us, 4 x 4 272 us, 8 x 8 277 us (profiles/README.md r02m);
+    // plain peer loads want more (2x B200: 4 x 4).
+    const int unroll = eu ? atoi(eu) : (multicast_buffer ? 2 : 4);
+    const int bpsm = eb && atoi(eb) > 0 ? atoi(eb) : (multicast_buffer ? 2 : 4);
     size_t blocks = ((n4 + world - 1) / world + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > (size_t)148 * bpsm) blocks = (size_t)148 * bpsm;
     if (blocks < 1) blocks = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
@@ -387,9 +398,15 @@ extern "C" int b3gs_peer_allreduce_fused(int world, int rank, float* const* peer
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
-#define B3_LAUNCH_FUSED(N, MM) \
-    e = cudaLaunchKernelEx(&cfg, peer_allreduce_fused_kernel<N, MM>, pp, multicast_buffer, world, rank, n4, flag_off_floats, \
+#define B3_LAUNCH_FUSED_U(N, MM, U) \
+    e = cudaLaunchKernelEx(&cfg, peer_allreduce_fused_kernel<N, MM, U>, pp, multicast_buffer, world, rank, n4, flag_off_floats, \
                            (uint32_t)epoch, scale)
+#define B3_LAUNCH_FUSED(N, MM)                                   \
+    do {                                                         \
+        if (unroll >= 8) B3_LAUNCH_FUSED_U(N, MM, 8);            \
+        else if (unroll <= 2) B3_LAUNCH_FUSED_U(N, MM, 2);       \
+        else B3_LAUNCH_FUSED_U(N, MM, 4);                        \
+    } while (0)
     if (multicast_buffer) {
         B3_LAUNCH_FUSED(1, true);
     } else {
@@ -405,6 +422,7 @@ extern "C" int b3gs_peer_allreduce_fused(int world, int rank, float* const* peer
         }
     }
 #undef B3_LAUNCH_FUSED
+#undef B3_LAUNCH_FUSED_U
     count_launch();
     return e == cudaSuccess ? 0 : -2;
 }

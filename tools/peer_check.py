@@ -65,6 +65,15 @@ for P, M in ((1001, 4), (200_000, 4), (300_001, 16), (1_000_000, 4)):
     peer._host_barriers = True
     t_host = time_it(lambda: peer.all_reduce(average=True))
     peer._host_barriers = False
+    sweep = ""
+    if os.environ.get("B3GS_AR_SWEEP") and P >= 200_000:          # tuning: requests in flight x resident blocks
+        for u in (2, 4, 8):
+            for b in (2, 4, 8):
+                os.environ["B3GS_AR_UNROLL"], os.environ["B3GS_AR_BPSM"] = str(u), str(b)
+                sweep += " u%d/b%d %.1f" % (u, b, time_it(lambda: peer.all_reduce(average=True), 30) * 1e3)
+        del os.environ["B3GS_AR_UNROLL"], os.environ["B3GS_AR_BPSM"]
+        if rank == 0:
+            print("  sweep (us):" + sweep, flush=True)
     if rank == 0:
         print("P=%d M=%d (%.1f MB) world=%d: rel diff vs NCCL %.2e, replicas bit-identical; fused kernel (%s) %.1f us, "
               "fused plain peer %.1f us, host-issued barriers %.1f us, NCCL %.1f us"
