@@ -847,7 +847,7 @@ struct TileBinArgs {
     const uint32_t* sorted_ids;
     const uint2* rects;
     uint32_t* table;              // [nb][T_pad]
-    uint8_t* wcount;              // [nb][kBinWarps][T_pad]
+    uint2* wcount;                // [nb][T_pad]: the kBinWarps (8) per-warp counts of a tile, one byte each
     uint32_t* point_list;
 };
 
@@ -868,25 +868,43 @@ static int bin_band_rows(int grid_x, int grid_y) {
     if (r > grid_y) r = grid_y;
     return r < 1 ? 1 : r;
 }
-// shared memory of one block: per-warp band counters, the batch's rectangle staging
-// (x0|y0<<16, w|h<<16, id), the lane map
-static size_t bin_smem_bytes(int B) {
-    return (size_t)kBinWarps * kBandTilesMax * 4 + (size_t)B * 12 + 33 * 32 * 4;
+// shared memory of one block: per-warp band counters (16-bit), the batch's rectangle staging
+// (x0|y0<<16, w|h<<16, id), the lane map, and — scatter — the band's output staging
+constexpr int kStageCap = 5888;          // instances of one (batch, band) staged in shared memory (mean 3840 at dtu)
+static size_t bin_smem_bytes(int B, bool scatter, bool staged) {
+    size_t n = (size_t)kBinWarps * kBandTilesMax * 2 + (size_t)B * 12 + 33 * 32 * 4 + 32 * 4;
+    if (scatter) n += (size_t)kBandTilesMax * 4 + (staged ? (size_t)kStageCap * 6 : (size_t)kBandTilesMax * 4);
+    return n;
 }
 
-template <bool kScatter>
+// count (kScatter = false): per-warp instance counts per tile of each band -> wcount (bytes),
+// block totals -> table.
+// scatter: the walk assigns every instance its slot in a BLOCK-LOCAL tile-major buffer of the band
+// (local_off[tile] + instances of earlier warps + rank in the warp: 16-bit counters), the ids are
+// staged there, and the block then copies the buffer out: consecutive threads write consecutive
+// slots of a tile's cell, so a warp store covers ~6 cells instead of 32 scattered words — the
+// scattered 4-byte global store was what bound the first version (profiles/README.md r02n).
+// kStaged = false: the walk stores straight to global memory (s_base[tile] + slot) — cheaper when a
+// (batch, tile) cell holds only ~2 instances and there is nothing to coalesce (fern: 0.093 vs 0.116 ms).
+template <bool kScatter, bool kStaged>
 __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x;
-    uint32_t* s_cnt = smem;                                  // [kBinWarps][kBandTilesMax]
-    uint32_t* s_xy = smem + kBinWarps * kBandTilesMax;       // B
+    uint32_t* s_xy = smem;                                   // B
     uint32_t* s_wh = s_xy + a.B;                             // B
     uint32_t* s_id = s_wh + a.B;                             // B
     uint32_t* s_map = s_id + a.B;                            // [33][32]: row | column << 8 | rows per step << 16
+    uint32_t* s_scan = s_map + 33 * 32;                      // 32 words for the block scan
+    uint32_t* s_base = s_scan + 32;                          // scatter: [kBandTilesMax] global position - local slot
+    constexpr int kCap = !kScatter ? 0 : (kStaged ? kStageCap : kBandTilesMax);   // unstaged: room for the wide path only
+    uint32_t* s_oid = s_base + (kScatter ? kBandTilesMax : 0);           // scatter: [kCap] staged ids
+    uint16_t* s_otile = reinterpret_cast<uint16_t*>(s_oid + kCap);       // scatter, staged: [kCap] their tiles
+    uint16_t* s_cnt = s_otile + (kStaged ? kCap : 0);        // [kBinWarps][kBandTilesMax]
     uint32_t* row = a.table + (size_t)b * a.T_pad;
-    uint8_t* wrow = a.wcount + (size_t)b * kBinWarps * a.T_pad;
-    uint32_t* cnt = s_cnt + warp * kBandTilesMax;            // this warp's counters
+    uint2* wrow = a.wcount + (size_t)b * a.T_pad;
+    static_assert(kBinWarps == 8, "the per-warp counts of a tile are packed into one 8-byte word");
+    uint16_t* cnt = s_cnt + warp * kBandTilesMax;            // this warp's counters
 
     // lane map: for a rectangle bw tiles wide, lane L handles column L % bw of rows
     // L / bw, L / bw + rows, ... with rows = 32 / bw whole rows per step (255: lane idle)
@@ -908,22 +926,66 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
     for (int by0 = 0; by0 < a.grid_y; by0 += a.band_rows) {
         const int by1 = min(a.grid_y, by0 + a.band_rows);
         const int band_start = by0 * a.grid_x, band_tiles = (by1 - by0) * a.grid_x;
+        uint32_t n_local = 0;
         if (kScatter) {
-            // start positions: table[b][tile] + the counts of the earlier warps
-            for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) {
-                uint32_t run = __ldg(row + band_start + k);
+            // local slots: exclusive scan over the band's tiles of the block's counts (blocked
+            // arrangement: a thread owns `per` consecutive tiles), then the warps' prefixes on top
+            const int per = (band_tiles + 32 * kBinWarps - 1) / (32 * kBinWarps);
+            const int k0 = threadIdx.x * per, k1 = min(band_tiles, k0 + per);
+            uint32_t acc = 0;
+            for (int k = k0; k < k1; k++) {
+                const uint2 c8 = __ldg(wrow + band_start + k);
+                // sum of the eight bytes: pairwise adds inside the words (each byte <= 255)
+                uint32_t v = (c8.x & 0x00ff00ffu) + ((c8.x >> 8) & 0x00ff00ffu) + (c8.y & 0x00ff00ffu) + ((c8.y >> 8) & 0x00ff00ffu);
+                acc += (v & 0xffffu) + (v >> 16);
+            }
+            const uint32_t inc = block_inclusive_scan(acc, s_scan, n_local);
+            uint32_t run = inc - acc;
+            for (int k = k0; k < k1; k++) {
+                s_base[k] = __ldg(row + band_start + k) - run;
+                const uint2 c8 = __ldg(wrow + band_start + k);
 #pragma unroll
                 for (int w = 0; w < kBinWarps; w++) {
-                    s_cnt[w * kBandTilesMax + k] = run;
-                    run += __ldg(wrow + (size_t)w * a.T_pad + band_start + k);
+                    s_cnt[w * kBandTilesMax + k] = (uint16_t)run;
+                    run += ((w < 4 ? c8.x : c8.y) >> (8 * (w & 3))) & 0xffu;
                 }
             }
         } else {
             for (int w = 0; w < kBinWarps; w++)
-                for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) s_cnt[w * kBandTilesMax + k] = 0u;
+                for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) s_cnt[w * kBandTilesMax + k] = 0;
         }
         __syncthreads();  // counters initialised (and, first band, the staging complete)
 
+        // More instances in this (batch, band) than 16-bit slots can number (a few hundred Gaussians
+        // that each cover most of the image): the warps take turns, in depth order, with 32-bit global
+        // positions kept where the ids would have been staged.  Correct, not fast, and rare.
+        const bool wide = kScatter && n_local > 65535u;      // block-uniform
+        if (wide) {
+            uint32_t* pos32 = s_oid;                         // kStageCap >= kBandTilesMax words
+            for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) pos32[k] = __ldg(row + band_start + k);
+            __syncthreads();
+            for (int turn = 0; turn < kBinWarps; turn++) {
+                if (warp == turn) {
+                    for (int c = w0; c < w1; c++) {          // one Gaussian at a time, lanes over its tiles
+                        const uint32_t xy = s_xy[c], w2 = s_wh[c];
+                        const int y0 = (int)(xy >> 16), cy0 = max(y0, by0), cy1 = min(y0 + (int)(w2 >> 16), by1);
+                        const int bw = (int)(w2 & 0xffffu), x0 = (int)(xy & 0xffffu);
+                        if (w2 == 0u || cy1 <= cy0) continue;
+                        const uint32_t gid = s_id[c];
+                        for (int j = lane; j < bw * (cy1 - cy0); j += 32) {
+                            const int yy = j / bw, xx = j - yy * bw;
+                            const uint32_t t = (uint32_t)((cy0 - by0 + yy) * a.grid_x + x0 + xx);
+                            const uint32_t pos = pos32[t];
+                            pos32[t] = pos + 1u;
+                            if (pos < a.cap) a.point_list[pos] = gid;
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+            continue;                                        // next band
+        }
         for (int c = w0; c < w1; c += 32) {
             // 32 Gaussians at once: clip to the band, precompute what the serial part needs
             uint32_t t0 = 0u, wh = 0u, g = 0u;
@@ -947,40 +1009,55 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
                 if (bw <= 32) {
                     const uint32_t m = s_map[bw * 32 + lane];
                     const int rows = (int)(m >> 16);
-                    uint32_t* pc = cnt + bt0 + ((m >> 8) & 0xffu);
+                    const uint32_t tcol = bt0 + ((m >> 8) & 0xffu);
                     for (int y = (int)(m & 0xffu); y < bh; y += rows) {
-                        const uint32_t pos = pc[y * a.grid_x];
-                        pc[y * a.grid_x] = pos + 1u;
-                        if (kScatter && pos < a.cap) a.point_list[pos] = bg;
+                        const uint32_t t = tcol + y * a.grid_x;
+                        const uint32_t slot = cnt[t];
+                        cnt[t] = (uint16_t)(slot + 1u);
+                        if (kScatter) {
+                            if (kStaged && slot < (uint32_t)kStageCap) { s_oid[slot] = bg; s_otile[slot] = (uint16_t)t; }
+                            else { const uint32_t pos = s_base[t] + slot; if (pos < a.cap) a.point_list[pos] = bg; }
+                        }
                     }
                 } else {
                     for (int y = 0; y < bh; y++) {
                         for (int x = lane; x < bw; x += 32) {
-                            uint32_t* q = cnt + bt0 + y * a.grid_x + x;
-                            const uint32_t pos = *q;
-                            *q = pos + 1u;
-                            if (kScatter && pos < a.cap) a.point_list[pos] = bg;
+                            const uint32_t t = bt0 + y * a.grid_x + x;
+                            const uint32_t slot = cnt[t];
+                            cnt[t] = (uint16_t)(slot + 1u);
+                            if (kScatter) {
+                                if (kStaged && slot < (uint32_t)kStageCap) { s_oid[slot] = bg; s_otile[slot] = (uint16_t)t; }
+                                else { const uint32_t pos = s_base[t] + slot; if (pos < a.cap) a.point_list[pos] = bg; }
+                            }
                         }
                     }
                 }
                 __syncwarp();  // the next Gaussian may touch the same counters
             }
         }
-        __syncthreads();  // every warp's counts are final / every warp has emitted
+        __syncthreads();  // every warp's counts are final / every warp has staged its ids
         if (!kScatter) {
             // per-warp counts (one byte: a warp owns <= 255 Gaussians) and the block total -> global
             for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) {
-                uint32_t sum = 0;
+                uint32_t sum = 0, lo = 0, hi = 0;
 #pragma unroll
                 for (int w = 0; w < kBinWarps; w++) {
                     const uint32_t v = s_cnt[w * kBandTilesMax + k];
-                    wrow[(size_t)w * a.T_pad + band_start + k] = (uint8_t)v;
+                    if (w < 4) lo |= v << (8 * w); else hi |= v << (8 * (w - 4));
                     sum += v;
                 }
+                wrow[band_start + k] = make_uint2(lo, hi);
                 row[band_start + k] = sum;
             }
-            __syncthreads();  // counters free for the next band
+        } else if (kStaged) {
+            // copy the band out: slot i of the local buffer goes to s_base[tile] + i
+            const uint32_t staged = min(n_local, (uint32_t)kStageCap);
+            for (uint32_t i = threadIdx.x; i < staged; i += 32 * kBinWarps) {
+                const uint32_t pos = s_base[s_otile[i]] + i;
+                if (pos < a.cap) a.point_list[pos] = s_oid[i];
+            }
         }
+        __syncthreads();  // counters and staging free for the next band
     }
 }
 
@@ -1059,7 +1136,7 @@ struct TileBinLayout {
         nchunks = (nb + kBinChunk - 1) / kBinChunk;
         size_t o = 0;
         table = o;      o = align_up(o + (size_t)nb * T_pad * 4, 256);
-        wcount = o;     o = align_up(o + (size_t)nb * kBinWarps * T_pad, 256);
+        wcount = o;     o = align_up(o + (size_t)nb * T_pad * 8, 256);
         chunk_sums = o; o = align_up(o + (size_t)nchunks * T_pad * 4, 256);
         tile_total = o; o = align_up(o + (size_t)T_pad * 4, 256);
         total = o;
@@ -1071,13 +1148,17 @@ static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t s
     uint32_t* table = reinterpret_cast<uint32_t*>(q + L.table);
     uint32_t* chunk_sums = reinterpret_cast<uint32_t*>(q + L.chunk_sums);
     uint32_t* tile_total = reinterpret_cast<uint32_t*>(q + L.tile_total);
-    const size_t smem = bin_smem_bytes(L.B);
+    // stage the output through shared memory when a (batch, tile) cell holds enough instances to coalesce
+    static const int forced_staged = [] { const char* e = getenv("B3GS_BIN_STAGED"); return e ? atoi(e) : -1; }();
+    const bool staged = forced_staged >= 0 ? forced_staged != 0 : (double)a.R >= 3.5 * (double)L.nb * (double)L.T;
+    const size_t smem_count = bin_smem_bytes(L.B, false, false), smem_scatter = bin_smem_bytes(L.B, true, staged);
     static thread_local int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != attr_dev) {  // opt in to more than 48 KB of dynamic shared memory, once per device
-        cudaFuncSetAttribute(tile_bins_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(tile_bins_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(tile_bins_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(tile_bins_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(tile_bins_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_dev = dev;
     }
     TileBinArgs k;
@@ -1085,15 +1166,16 @@ static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t s
     k.band_rows = L.band_rows;
     k.cap = (uint32_t)a.R;
     k.sorted_ids = a.sorted_ids; k.rects = a.rects; k.table = table; k.point_list = a.point_list;
-    k.wcount = reinterpret_cast<uint8_t*>(q + L.wcount);
+    k.wcount = reinterpret_cast<uint2*>(q + L.wcount);
     cudaError_t e = cudaMemsetAsync(tile_total, 0, (size_t)L.T_pad * 4, stream);
     if (e != cudaSuccess) return e;
-    tile_bins_kernel<false><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
+    tile_bins_kernel<false, false><<<L.nb, 32 * kBinWarps, smem_count, stream>>>(k);
     const dim3 grid((L.T + 255) / 256, L.nchunks);
     bin_chunk_sums<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
     bin_tile_scan<<<1, 1024, 0, stream>>>(tile_total, L.T, a.ranges, k.cap);
     bin_apply<<<grid, 256, 0, stream>>>(table, L.nb, L.T, L.T_pad, chunk_sums, tile_total);
-    tile_bins_kernel<true><<<L.nb, 32 * kBinWarps, smem, stream>>>(k);
+    if (staged) tile_bins_kernel<true, true><<<L.nb, 32 * kBinWarps, smem_scatter, stream>>>(k);
+    else tile_bins_kernel<true, false><<<L.nb, 32 * kBinWarps, smem_scatter, stream>>>(k);
     count_launch(5);
     return cudaGetLastError();
 }

@@ -559,3 +559,25 @@ def test_nosync_forward_equals_exact_forward_and_recovers_from_overflow(host):
             means3D=scene.means3D, means2D=torch.zeros_like(scene.means3D), opacities=scene.opacities,
             shs=scene.shs, scales=scene.scales, rotations=scene.rotations)[0]
     assert torch.equal(c, exact["color"])
+
+
+@pytest.mark.gpu
+def test_binning_with_screen_filling_gaussians(nat, ref, dev):
+    """A few thousand Gaussians that each cover most of the image: more instances per (batch of
+    depth-ordered Gaussians, band of tile rows) than the direct tile binning's 16-bit slots can
+    number — its wide path (binning.cu) — and lists of thousands of entries in every tile."""
+    W, H, P = 512, 384, 3000
+    scene = make_scene(P, seed=61, scale_lo=0.8, scale_hi=2.0)
+    scene.opacities[:] = 0.02 + 0.05 * scene.opacities          # faint: no early termination, long walks
+    scene = scene.to(dev)
+    cam = make_camera(W, H, azimuth=0.5).to(dev)
+    bg = torch.tensor([0.1, 0.1, 0.1], device=dev)
+    fn, fr = util.raw_forward(nat, scene, cam, bg), util.raw_forward(ref, scene, cam, bg)
+    inn, inr = util.internals(nat, fn, P, W, H), util.internals(ref, fr, P, W, H)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert fn["R"] == fr["R"] and fn["R"] > 512 * 65535 // 64 and fn["R"] > 0.5 * int((fr["radii"] > 0).sum()) * T
+    assert (inn["point_list"] == inr["point_list"]).all()
+    assert (inn["ranges"] == inr["ranges"]).all()
+    assert (inn["n_contrib"] == inr["n_contrib"]).all()
+    for k in ("color", "depth", "alpha"):
+        assert (_bits(fn[k]) == _bits(fr[k])).all(), k
