@@ -54,10 +54,8 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
     c[5] = M.m[2][0] * M.m[2][0] + M.m[2][1] * M.m[2][1] + M.m[2][2] * M.m[2][2];
 }
 
-// 3 blocks/SM at 80 registers; 4 / 5 / 6 spill more and are slower (B200, lego:
-// 27.4 / 29.9 / 37.6 / 41.7 us) although 6 would fit the grid into one wave.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) preprocess_backward_kernel(PreBackwardArgs p) {
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kernel(PreBackwardArgs p) {
     const int idx = p.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.first + p.count) return;
     const size_t i = (size_t)idx;
@@ -390,9 +388,17 @@ void launch_preprocess_backward(const PreBackwardArgs& a0, cudaStream_t stream, 
     a.first = first;
     a.count = count < 0 ? a.P - first : count;
     if (a.count <= 0) return;
-    static const int occ = [] { const char* e = getenv("B3GS_PREBWD_OCC"); return e ? atoi(e) : 3; }();
-    if (occ == 2) preprocess_backward_kernel<2><<<(a.count + 255) / 256, 256, 0, stream>>>(a);
-    else preprocess_backward_kernel<3><<<(a.count + 255) / 256, 256, 0, stream>>>(a);
+    // threads per block x minimum blocks per SM (register cap); B3GS_PREBWD_SHAPE = 0..4 overrides.
+    // Measured on B200, 1M / 200k Gaussians: 256x3 (80 regs, 184 B spilled) 87.0 / 27.2 us, 128x6 80.5 / 25.8,
+    // 128x5 84.5 / 27.1, 128x4 (no spills) 90.8 / 27.1, 64x10 (96 regs, 40 B spilled) 78.7 / 25.2.
+    static const int shape = [] { const char* e = getenv("B3GS_PREBWD_SHAPE"); return e ? atoi(e) : 4; }();
+    switch (shape) {
+        case 1: preprocess_backward_kernel<128, 6><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 85 regs
+        case 2: preprocess_backward_kernel<128, 5><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 102 regs
+        case 3: preprocess_backward_kernel<128, 4><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 128 regs
+        case 4: preprocess_backward_kernel<64, 10><<<(a.count + 63) / 64, 64, 0, stream>>>(a); break;      // 102 regs
+        default: preprocess_backward_kernel<256, 3><<<(a.count + 255) / 256, 256, 0, stream>>>(a); break;  // 80 regs
+    }
     count_launch();
 }
 
