@@ -121,33 +121,37 @@ constexpr int kCountSlots = 256;
 struct CountSlot {
     cudaEvent_t ev = nullptr;
     int* word = nullptr;        // pinned
-    int device = -1;
     unsigned generation = 0;
 };
+struct CountRing {              // one per device, allocated as a whole on first use: nothing is
+    bool ready = false;         // allocated later, so a forward inside a CUDA-graph capture is legal
+    unsigned next = 0;
+    CountSlot slots[kCountSlots];
+};
 static std::mutex g_slot_mu;
-static CountSlot g_slots[kCountSlots];
-static unsigned g_slot_next = 0;
+static CountRing g_rings[kMaxDevices];
 
-// returns the ticket (generation << 8 | slot) or -1
+// returns the ticket (device << 24 | generation << 8 | slot) or -1
 static int acquire_count_slot(CountSlot** out) {
     const int dev = current_device();
     if (dev < 0) return -1;
     std::lock_guard<std::mutex> lk(g_slot_mu);
-    const unsigned idx = g_slot_next++ % kCountSlots;
-    CountSlot& s = g_slots[idx];
-    if (s.ev && s.device != dev) {   // events belong to a device
-        cudaEventDestroy(s.ev);
-        s.ev = nullptr;
+    CountRing& r = g_rings[dev];
+    if (!r.ready) {
+        int* block = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&block), sizeof(int) * 4 * kCountSlots, cudaHostAllocDefault) != cudaSuccess)
+            return -1;
+        for (int i = 0; i < kCountSlots; i++) {
+            if (cudaEventCreateWithFlags(&r.slots[i].ev, cudaEventDisableTiming) != cudaSuccess) return -1;
+            r.slots[i].word = block + 4 * i;
+        }
+        r.ready = true;
     }
-    if (!s.ev && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) { s.ev = nullptr; return -1; }
-    if (!s.word && cudaHostAlloc(reinterpret_cast<void**>(&s.word), sizeof(int) * 4, cudaHostAllocDefault) != cudaSuccess) {
-        s.word = nullptr;
-        return -1;
-    }
-    s.device = dev;
-    s.generation = (s.generation + 1) & 0x3fffffu;
+    const unsigned idx = r.next++ % kCountSlots;
+    CountSlot& s = r.slots[idx];
+    s.generation = (s.generation + 1) & 0xffffu;
     *out = &s;
-    return (int)((s.generation << 8) | idx);
+    return (int)(((unsigned)dev << 24) | (s.generation << 8) | idx);
 }
 
 // ---- optional per-stage device timing (bench.py roofline) ---------------------
@@ -414,8 +418,11 @@ int b3gs_count_wait(int ticket, int* num_rendered) {
     int* word;
     {
         std::lock_guard<std::mutex> lk(g_slot_mu);
-        const CountSlot& s = g_slots[ticket & 0xff];
-        if (!s.ev || s.generation != ((unsigned)ticket >> 8))
+        const unsigned dev = (unsigned)ticket >> 24;
+        if (dev >= (unsigned)kMaxDevices || !g_rings[dev].ready)
+            return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_count_wait: bad ticket");
+        const CountSlot& s = g_rings[dev].slots[ticket & 0xff];
+        if (s.generation != (((unsigned)ticket >> 8) & 0xffffu))
             return fail(B3GS_ERR_INVALID_ARGUMENT, "b3gs_count_wait: the ticket has expired (more than 256 later forwards)");
         ev = s.ev; word = s.word;
     }

@@ -581,3 +581,59 @@ def test_binning_with_screen_filling_gaussians(nat, ref, dev):
     assert (inn["n_contrib"] == inr["n_contrib"]).all()
     for k in ("color", "depth", "alpha"):
         assert (_bits(fn[k]) == _bits(fr[k])).all(), k
+
+
+@pytest.mark.gpu
+def test_forward_and_backward_capture_into_a_cuda_graph(nat, dev):
+    """With the no-sync forward nothing on the path blocks the host, so forward + backward can be
+    captured into ONE CUDA graph (12 kernel nodes, the cooperative depth sort included) and replayed
+    with new camera matrices written into the captured input tensors: same images bit for bit, same
+    gradients up to the order of the float REDs."""
+    W, H, P = 400, 300, 30000
+    scene = make_scene(P, seed=71).to(dev)
+    cams = [make_camera(W, H, azimuth=a).to(dev) for a in (0.3, 1.4)]
+    bg = torch.tensor([0.2, 0.3, 0.1], device=dev)
+    gc, gd, ga = (t.to(dev) for t in make_pixel_grads(W, H, 72))
+    e = torch.empty(0)
+    view, proj, center = (t.clone() for t in (cams[0].world_view_transform, cams[0].full_proj_transform,
+                                              cams[0].camera_center))
+
+    def forward(nosync_capacity=None):
+        args = (bg, scene.means3D, e, scene.opacities, scene.scales, scene.rotations, 1.0, e, view, proj,
+                cams[0].tanfovx, cams[0].tanfovy, H, W, scene.shs, scene.sh_degree, center, False, False)
+        return (nat.rasterize_gaussians(*args) if nosync_capacity is None
+                else nat.rasterize_gaussians_nosync(nosync_capacity, *args))
+
+    def backward(out, R):
+        return nat.rasterize_gaussians_backward(bg, scene.means3D, out[4], e, scene.scales, scene.rotations, 1.0, e, view,
+                                                proj, cams[0].tanfovx, cams[0].tanfovy, gc, gd, ga, scene.shs,
+                                                scene.sh_degree, center, out[5], R, out[6], out[7], out[3], False)
+
+    def set_camera(c):
+        view.copy_(c.world_view_transform); proj.copy_(c.full_proj_transform); center.copy_(c.camera_center)
+
+    eager = []
+    for c in cams:                                   # exact, eager: what every replay must reproduce
+        set_camera(c)
+        out = forward()
+        eager.append((out, [g.clone() for g in backward(out, out[0])]))
+    capacity = 2 * max(o[0][0] for o in eager)
+    side = torch.cuda.Stream(device=dev)             # warm-up on a side stream, as torch's capture recipe asks
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        out = forward(capacity)
+        backward(out, eager[-1][0][0])
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out = forward(capacity)
+        g_grads = backward(g_out, capacity // 2)      # R only steers the backward's kernel shape
+    for c, (out, grads) in zip(cams, eager):
+        set_camera(c)
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in (1, 2, 3, 4):                       # colour, depth, alpha, radii
+            assert torch.equal(g_out[k], out[k]), k
+        for a, b in zip(g_grads, grads):
+            assert util.rel_err(a, b) <= 2e-5
