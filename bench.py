@@ -356,6 +356,24 @@ def dp_selfcheck(arm, dev, rank, world):
             bucket.overlap = keep
     out["sink_exchange_vs_gathered_max_rel"] = worst
     out["replicas_identical_gradients"] = identical
+    # (c') raw-parameter models: dp.ParameterBucket in symmetric memory — autograd accumulates into
+    # slices of one flat buffer, one fused exchange follows
+    gp = torch.Generator(device="cpu").manual_seed(99)
+    params = [torch.nn.Parameter(torch.randn(shape, generator=gp).to(dev)) for shape in ((P, 3), (P, 1, 3), (P, 1), (P, 4))]
+    pb = dp.ParameterBucket(params, peer=True)
+    pb.attach()
+    gl = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    weights = [torch.randn(p_.shape, generator=gl).to(dev) for p_ in params]
+    sum((p_ * w_).sum() + 0.5 * ((p_ * w_) ** 2).sum() for p_, w_ in zip(params, weights)).backward()
+    expect = []
+    for p_, w_ in zip(params, weights):
+        t = (w_ + (p_.detach() * w_) * w_).clone()
+        dist.all_reduce(t)
+        expect.append(t / world)
+    pb.all_reduce(average=True)
+    torch.cuda.synchronize()
+    out["parameter_bucket_vs_nccl_max_rel"] = max(float((p_.grad - e_).abs().max() / e_.abs().max()) for p_, e_ in zip(params, expect))
+    out["parameter_bucket_replicas_identical"] = bool(dp.replicas_identical([p_.grad for p_ in params]))
     # (d) densification in lockstep
     dp.seed_lockstep(777)
     xyz, scaling = scene.means3D.clone(), torch.log(scene.scales)
@@ -368,7 +386,8 @@ def dp_selfcheck(arm, dev, rank, world):
     out["densify_lockstep_identical"] = bool(dp.replicas_identical([new_xyz, r2]))
     out["densify_cloned"] = int(sel.sum())
     ok = (out["peer_vs_nccl_max_rel"] < 1e-5 and out["replicas_identical_after_exchange"]
-          and worst < 1e-4 and out["replicas_identical_gradients"] and out["densify_lockstep_identical"])
+          and worst < 1e-4 and out["replicas_identical_gradients"] and out["densify_lockstep_identical"]
+          and out["parameter_bucket_vs_nccl_max_rel"] < 1e-5 and out["parameter_bucket_replicas_identical"])
     out["ok"] = bool(ok)
     return out
 

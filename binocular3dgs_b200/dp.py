@@ -316,7 +316,7 @@ class ParameterBucket:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
         if self._inner is not None:
-            self._inner.all_reduce(average)
+            self._inner.all_reduce(average=average)
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if average:
