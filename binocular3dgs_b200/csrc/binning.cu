@@ -35,6 +35,7 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -836,13 +837,17 @@ static int tile_passes(int T) {
 // output either way: a stable distribution by tile of a (depth, id)-ordered sequence.
 constexpr int kBinChunk = 32;            // batches per scan chunk
 constexpr int kBinWarps = 8;             // warps per block = sub-batches per batch
-constexpr int kBandTilesMax = 1152;      // counters of one band: 8 x 4.5 KB of shared memory (4 blocks per SM)
-constexpr int kBandRowsMax = 200;        // rows of a band (the lane map stores a row in 8 bits)
-constexpr int kMaxBinBatch = 1024;       // Gaussians per batch: 128 per warp (one-byte counts hold <= 255)
+constexpr int kBandTilesMax = 2040;      // widest tile row / largest band the direct path takes (a width is packed in 11 bits)
+constexpr int kBandTilesDefault = 1152;  // counters of one band: 8 x 2.25 KB of shared memory
+constexpr int kBinPer = 8;               // scatter: tiles per thread of a band's table rows kept in registers (kBandTilesMax / 256)
+constexpr int kBandRowsMax = 200;        // rows of a band (a clipped height is packed in 8 bits, 255 = lane idle)
+constexpr int kMaxBinBatch = 2040;       // Gaussians per batch: <= 255 per warp (one-byte per-warp counts)
 constexpr int kMinBinTiles = 0;          // smaller grids would go through emit + radix (none: the direct path wins or ties at all BASELINE sizes)
 
 struct TileBinArgs {
     int P, B, nb, T, T_pad, grid_x, grid_y, band_rows;
+    int band_max;                 // counters per warp (>= tiles of a band)
+    int stage_cap;                // scatter: slots of the block-local staging buffer
     uint32_t cap;                 // point_list capacity (instances)
     const uint32_t* sorted_ids;
     const uint2* rects;
@@ -851,39 +856,63 @@ struct TileBinArgs {
     uint32_t* point_list;
 };
 
-// Batch size: 512 / 1024 Gaussians per block (64 / 128 per warp) give 400-1000 blocks at the
+// Batch size: 512 / 768 Gaussians per block (64 / 96 per warp) give 400-1300 blocks at the
 // BASELINE sizes; doubled while the table would outweigh the instance list itself (many tiles, few
 // instances).  B3GS_BIN_BATCH overrides (tuning).
 static int bin_batch_size(int P, int R, int T_pad) {
     static const int forced = [] { const char* e = getenv("B3GS_BIN_BATCH"); return e ? atoi(e) : 0; }();
-    if (forced >= 256 && forced <= kMaxBinBatch && (forced & (forced - 1)) == 0) return forced;
-    int B = P >= (1 << 19) ? 1024 : 512;   // measured: 1M Gaussians 0.593 vs 0.642 ms, 200k 0.088 vs 0.117 ms
+    if (forced >= 256 && forced <= kMaxBinBatch && forced % 8 == 0) return forced;
+    // measured (profiles/README.md r02aa/r02ac): 1M Gaussians 0.354 (768) vs 0.374 (1024) vs 0.41 (640) ms;
+    // 200k 0.073 (384: 521 blocks) vs 0.080 (512: 391 blocks, less than one wave of 3 x 148) vs 0.103 (768) ms;
+    // 300k 0.089 (512) vs 0.106 (384) ms  ->  the largest size that still fills one wave of the scatter
+    int B = 256;
+    for (int cand : {768, 512, 384}) {
+        if (cand == 768 && P < (1 << 19)) continue;
+        if ((P + cand - 1) / cand >= 444) { B = cand; break; }
+    }
     const size_t budget = (size_t)(R > 0 ? R : 0) * 8 + ((size_t)32 << 20);
-    while (B < kMaxBinBatch && (size_t)((P + B - 1) / B) * T_pad * 12 > budget) B *= 2;
+    while (B < 1024 && (size_t)((P + B - 1) / B) * T_pad * 12 > budget) B *= 2;
     return B;
 }
+static int bin_band_max() {   // B3GS_BIN_BAND: tiles per band (tuning)
+    static const int v = [] { const char* e = getenv("B3GS_BIN_BAND"); const int x = e ? atoi(e) : 0;
+                              return x >= 64 && x <= kBandTilesMax ? (x + 1) & ~1 : kBandTilesDefault; }();
+    return v;
+}
 static int bin_band_rows(int grid_x, int grid_y) {
-    int r = kBandTilesMax / grid_x;
+    int r = bin_band_max() / grid_x;
     if (r > kBandRowsMax) r = kBandRowsMax;
     if (r > grid_y) r = grid_y;
     return r < 1 ? 1 : r;
 }
 // shared memory of one block: per-warp band counters (16-bit), the batch's rectangle staging
-// (x0|y0<<16, w|h<<16, id), the lane map, and — scatter — the band's output staging
-constexpr int kStageCap = 5888;          // instances of one (batch, band) staged in shared memory (mean 3840 at dtu)
-static size_t bin_smem_bytes(int B, bool scatter, bool staged) {
-    size_t n = (size_t)kBinWarps * kBandTilesMax * 2 + (size_t)B * 12 + 33 * 32 * 4 + 32 * 4;
-    if (scatter) n += (size_t)kBandTilesMax * 4 + (staged ? (size_t)kStageCap * 6 : (size_t)kBandTilesMax * 4);
+// (x0|y0<<16, w|h<<16, id), and — scatter — the band's output staging
+static size_t bin_smem_bytes(int B, int band_max, bool scatter, int stage_cap) {   // stage_cap = 0: unstaged
+    size_t n = (size_t)kBinWarps * band_max * 2 + (size_t)B * 12 + 32 * 4;
+    if (scatter) n += (size_t)band_max * 4 + (size_t)(stage_cap ? stage_cap : band_max) * 4;
     return n;
+}
+// Staging slots of the scatter (one word each: batch-local Gaussian index << 16 | tile of the band):
+// whatever three blocks per SM leave (228 KB per SM, 1 KB reserved per block) — at dtu 1.5x the
+// mean of a (batch, band); instances beyond it are stored directly.  B3GS_BIN_STAGE overrides.
+static int bin_stage_cap(int B, int band_max) {
+    static const int forced = [] { const char* e = getenv("B3GS_BIN_STAGE"); const int x = e ? atoi(e) : 0;
+                                   return x >= 256 && x <= 32768 ? x : 0; }();
+    const long fixed = (long)bin_smem_bytes(B, band_max, true, 0) - (long)band_max * 4;
+    long v = forced ? forced : ((228 * 1024) / 3 - 1024 - fixed) / 4;
+    if (v > 32768) v = 32768;
+    return v > band_max ? (int)v : band_max;   // the wide path keeps band_max 32-bit positions there
 }
 
 // count (kScatter = false): per-warp instance counts per tile of each band -> wcount (bytes),
 // block totals -> table.
 // scatter: the walk assigns every instance its slot in a BLOCK-LOCAL tile-major buffer of the band
-// (local_off[tile] + instances of earlier warps + rank in the warp: 16-bit counters), the ids are
-// staged there, and the block then copies the buffer out: consecutive threads write consecutive
-// slots of a tile's cell, so a warp store covers ~6 cells instead of 32 scattered words — the
-// scattered 4-byte global store was what bound the first version (profiles/README.md r02n).
+// (local_off[tile] + instances of earlier warps + rank in the warp: 16-bit counters) and stages one
+// word there (index of the Gaussian in the batch << 16 | tile of the band); the block then copies
+// the buffer out: consecutive threads write consecutive slots of a tile's cell, so a warp store
+// covers ~6 cells instead of 32 scattered words — the scattered 4-byte global store was what bound
+// the first version (profiles/README.md r02n).  The band's rows of the table and of the per-warp
+// counts are loaded into registers one band ahead (ncu r02ab: 12 % of the warp samples waited on them).
 // kStaged = false: the walk stores straight to global memory (s_base[tile] + slot) — cheaper when a
 // (batch, tile) cell holds only ~2 instances and there is nothing to coalesce (fern: 0.093 vs 0.116 ms).
 template <bool kScatter, bool kStaged>
@@ -891,27 +920,37 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x;
-    uint32_t* s_xy = smem;                                   // B
+    const int band_max = a.band_max;
+    const int kCap = !kScatter ? 0 : (kStaged ? a.stage_cap : band_max);   // unstaged: room for the wide path only
+    uint32_t* s_oid = smem;                                  // scatter: [kCap] staged (index in the batch << 16 | tile); first, so
+                                                             // that the walk's store address is slot * 4 + a constant
+    uint32_t* s_base = s_oid + kCap;                         // scatter: [band_max] global position - local slot
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_base + (kScatter ? band_max : 0));   // [kBinWarps][band_max], 16-byte aligned
+    uint32_t* s_xy = reinterpret_cast<uint32_t*>(s_cnt + kBinWarps * band_max);          // B
     uint32_t* s_wh = s_xy + a.B;                             // B
     uint32_t* s_id = s_wh + a.B;                             // B
-    uint32_t* s_map = s_id + a.B;                            // [33][32]: row | column << 8 | rows per step << 16
-    uint32_t* s_scan = s_map + 33 * 32;                      // 32 words for the block scan
-    uint32_t* s_base = s_scan + 32;                          // scatter: [kBandTilesMax] global position - local slot
-    constexpr int kCap = !kScatter ? 0 : (kStaged ? kStageCap : kBandTilesMax);   // unstaged: room for the wide path only
-    uint32_t* s_oid = s_base + (kScatter ? kBandTilesMax : 0);           // scatter: [kCap] staged ids
-    uint16_t* s_otile = reinterpret_cast<uint16_t*>(s_oid + kCap);       // scatter, staged: [kCap] their tiles
-    uint16_t* s_cnt = s_otile + (kStaged ? kCap : 0);        // [kBinWarps][kBandTilesMax]
+    uint32_t* s_scan = s_id + a.B;                           // 32 words for the block scan
     uint32_t* row = a.table + (size_t)b * a.T_pad;
     uint2* wrow = a.wcount + (size_t)b * a.T_pad;
     static_assert(kBinWarps == 8, "the per-warp counts of a tile are packed into one 8-byte word");
-    uint16_t* cnt = s_cnt + warp * kBandTilesMax;            // this warp's counters
+    uint16_t* cnt = s_cnt + warp * band_max;                 // this warp's counters
 
-    // lane map: for a rectangle bw tiles wide, lane L handles column L % bw of rows
-    // L / bw, L / bw + rows, ... with rows = 32 / bw whole rows per step (255: lane idle)
-    for (int bw = 1 + warp; bw <= 32; bw += kBinWarps) {
-        const int rows = 32 / bw, ry = lane / bw;
-        s_map[bw * 32 + lane] = (ry < rows ? (uint32_t)ry : 255u) | ((uint32_t)(lane - ry * bw) << 8) | ((uint32_t)rows << 16);
-    }
+    // scatter: this thread's tiles of the band's table / per-warp-count rows, loaded one band ahead
+    uint2 c8[kBinPer];
+    uint32_t rw[kBinPer];
+    auto fetch = [&](int by0) {
+        const int by1 = min(a.grid_y, by0 + a.band_rows);
+        const int start = by0 * a.grid_x, tiles = (by1 - by0) * a.grid_x;
+        const int per = (tiles + 32 * kBinWarps - 1) / (32 * kBinWarps);
+        const int k0 = threadIdx.x * per, k1 = min(tiles, k0 + per);
+#pragma unroll
+        for (int j = 0; j < kBinPer; j++) {
+            const bool on = k0 + j < k1;
+            c8[j] = on ? __ldg(wrow + start + k0 + j) : make_uint2(0u, 0u);
+            rw[j] = on ? __ldg(row + start + k0 + j) : 0u;
+        }
+    };
+    if (kScatter) fetch(0);
     // stage the batch: rectangles (and ids) in depth order
     const int i0 = b * a.B, n = min(a.P, i0 + a.B) - i0;
     for (int k = threadIdx.x; k < n; k += 32 * kBinWarps) {
@@ -920,6 +959,28 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
         s_xy[k] = r.x; s_wh[k] = r.y;
         if (kScatter) s_id[k] = g;
     }
+    // The walk's shared-window addresses and loop constants, pinned in registers (left to the compiler they
+    // are re-derived from the constant bank / SR_CgaCtaId for every instance: ncu r02ac, 6 % of the samples).
+    uint32_t cnt_sa = (uint32_t)__cvta_generic_to_shared(cnt), oid_sa = (uint32_t)__cvta_generic_to_shared(s_oid);
+    int gx = a.grid_x;
+    uint32_t stage_slots = (uint32_t)kCap;
+    asm volatile("" : "+r"(gx), "+r"(stage_slots), "+r"(cnt_sa), "+r"(oid_sa));
+    // one instance: rank = this warp's counter of the tile; scatter: stage it (or store it directly)
+    auto touch = [&](uint32_t t, uint32_t packed, uint32_t bg) {
+        const uint32_t ca = cnt_sa + 2u * t;
+        unsigned short slot16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(slot16) : "r"(ca) : "memory");
+        const uint32_t slot = slot16;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(ca), "h"((unsigned short)(slot + 1u)) : "memory");
+        if (kScatter) {
+            if (kStaged && slot < stage_slots) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(oid_sa + 4u * slot), "r"(packed | t) : "memory");
+            } else {
+                const uint32_t pos = s_base[t] + slot;
+                if (pos < a.cap) a.point_list[pos] = kStaged ? s_id[packed >> 16] : bg;
+            }
+        }
+    };
     const int sub = a.B / kBinWarps;                          // Gaussians per warp
     const int w0 = warp * sub, w1 = min(n, w0 + sub);
 
@@ -933,26 +994,31 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
             const int per = (band_tiles + 32 * kBinWarps - 1) / (32 * kBinWarps);
             const int k0 = threadIdx.x * per, k1 = min(band_tiles, k0 + per);
             uint32_t acc = 0;
-            for (int k = k0; k < k1; k++) {
-                const uint2 c8 = __ldg(wrow + band_start + k);
-                // sum of the eight bytes: pairwise adds inside the words (each byte <= 255)
-                uint32_t v = (c8.x & 0x00ff00ffu) + ((c8.x >> 8) & 0x00ff00ffu) + (c8.y & 0x00ff00ffu) + ((c8.y >> 8) & 0x00ff00ffu);
+#pragma unroll
+            for (int j = 0; j < kBinPer; j++) {
+                // sum of the eight bytes: pairwise adds inside the words (each byte <= 255; zero past k1)
+                const uint32_t v = (c8[j].x & 0x00ff00ffu) + ((c8[j].x >> 8) & 0x00ff00ffu) + (c8[j].y & 0x00ff00ffu) + ((c8[j].y >> 8) & 0x00ff00ffu);
                 acc += (v & 0xffffu) + (v >> 16);
             }
             const uint32_t inc = block_inclusive_scan(acc, s_scan, n_local);
             uint32_t run = inc - acc;
-            for (int k = k0; k < k1; k++) {
-                s_base[k] = __ldg(row + band_start + k) - run;
-                const uint2 c8 = __ldg(wrow + band_start + k);
 #pragma unroll
-                for (int w = 0; w < kBinWarps; w++) {
-                    s_cnt[w * kBandTilesMax + k] = (uint16_t)run;
-                    run += ((w < 4 ? c8.x : c8.y) >> (8 * (w & 3))) & 0xffu;
+            for (int j = 0; j < kBinPer; j++) {
+                const int k = k0 + j;
+                if (k < k1) {
+                    s_base[k] = rw[j] - run;
+#pragma unroll
+                    for (int w = 0; w < kBinWarps; w++) {
+                        s_cnt[w * band_max + k] = (uint16_t)run;
+                        run += ((w < 4 ? c8[j].x : c8[j].y) >> (8 * (w & 3))) & 0xffu;
+                    }
                 }
             }
+            if (by1 < a.grid_y) fetch(by1);   // the next band's rows arrive while this band is walked
         } else {
-            for (int w = 0; w < kBinWarps; w++)
-                for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) s_cnt[w * kBandTilesMax + k] = 0;
+            // zero the eight counter rows (contiguous, 16-byte aligned: B is a multiple of 8)
+            uint4* z = reinterpret_cast<uint4*>(s_cnt);
+            for (int k = threadIdx.x; k < band_max; k += 32 * kBinWarps) z[k] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();  // counters initialised (and, first band, the staging complete)
 
@@ -961,7 +1027,7 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
         // positions kept where the ids would have been staged.  Correct, not fast, and rare.
         const bool wide = kScatter && n_local > 65535u;      // block-uniform
         if (wide) {
-            uint32_t* pos32 = s_oid;                         // kStageCap >= kBandTilesMax words
+            uint32_t* pos32 = s_oid;                         // kCap >= band_max words
             for (int k = threadIdx.x; k < band_tiles; k += 32 * kBinWarps) pos32[k] = __ldg(row + band_start + k);
             __syncthreads();
             for (int turn = 0; turn < kBinWarps; turn++) {
@@ -995,8 +1061,11 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
                 const int cy0 = max(y0, by0), cy1 = min(y1, by1);
                 if (w2 != 0u && cy1 > cy0) {
                     t0 = (uint32_t)((cy0 - by0) * a.grid_x) + (xy & 0xffffu);
-                    wh = (w2 & 0xffffu) | ((uint32_t)(cy1 - cy0) << 16);
-                    if (kScatter) g = s_id[c + lane];
+                    // width (11 bits) | clipped height << 11 (8 bits) | ceil-reciprocal of the width << 19:
+                    // (L * inv) >> 10 == L / width exactly for L <= 32, width <= 32
+                    const uint32_t bw = w2 & 0xffffu;
+                    wh = bw | ((uint32_t)(cy1 - cy0) << 11) | (bw <= 32u ? (__float2uint_rz(__frcp_ru((float)bw) * 1024.f) + 1u) << 19 : 0u);   // 1024 / bw + 1 without the division routine
+                    if (kScatter && !kStaged) g = s_id[c + lane];
                 }
             }
             unsigned nz = __ballot_sync(full, wh != 0u);
@@ -1004,31 +1073,19 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
                 const int src = __ffs(nz) - 1;
                 nz &= nz - 1;
                 const uint32_t bt0 = __shfl_sync(full, t0, src), bwh = __shfl_sync(full, wh, src);
-                const uint32_t bg = kScatter ? __shfl_sync(full, g, src) : 0u;
-                const int bw = (int)(bwh & 0xffffu), bh = (int)(bwh >> 16);
+                const uint32_t bg = (kScatter && !kStaged) ? __shfl_sync(full, g, src) : 0u;
+                const uint32_t packed = (uint32_t)(c + src) << 16;   // staged: the Gaussian's index in the batch
+                const int bw = (int)(bwh & 0x7ffu), bh = (int)((bwh >> 11) & 0xffu);
                 if (bw <= 32) {
-                    const uint32_t m = s_map[bw * 32 + lane];
-                    const int rows = (int)(m >> 16);
-                    const uint32_t tcol = bt0 + ((m >> 8) & 0xffu);
-                    for (int y = (int)(m & 0xffu); y < bh; y += rows) {
-                        const uint32_t t = tcol + y * a.grid_x;
-                        const uint32_t slot = cnt[t];
-                        cnt[t] = (uint16_t)(slot + 1u);
-                        if (kScatter) {
-                            if (kStaged && slot < (uint32_t)kStageCap) { s_oid[slot] = bg; s_otile[slot] = (uint16_t)t; }
-                            else { const uint32_t pos = s_base[t] + slot; if (pos < a.cap) a.point_list[pos] = bg; }
-                        }
-                    }
+                    // lane L handles column L % bw of rows L / bw, L / bw + rows, ... (rows = 32 / bw whole rows per step)
+                    const uint32_t inv = bwh >> 19;
+                    const int ry = (int)(((uint32_t)lane * inv) >> 10), rows = (int)((32u * inv) >> 10);
+                    const uint32_t tcol = bt0 + (uint32_t)(lane - ry * bw);
+                    for (int y = ry < rows ? ry : 255; y < bh; y += rows) touch(tcol + y * gx, packed, bg);
                 } else {
                     for (int y = 0; y < bh; y++) {
                         for (int x = lane; x < bw; x += 32) {
-                            const uint32_t t = bt0 + y * a.grid_x + x;
-                            const uint32_t slot = cnt[t];
-                            cnt[t] = (uint16_t)(slot + 1u);
-                            if (kScatter) {
-                                if (kStaged && slot < (uint32_t)kStageCap) { s_oid[slot] = bg; s_otile[slot] = (uint16_t)t; }
-                                else { const uint32_t pos = s_base[t] + slot; if (pos < a.cap) a.point_list[pos] = bg; }
-                            }
+                            touch(bt0 + y * gx + x, packed, bg);
                         }
                     }
                 }
@@ -1042,7 +1099,7 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
                 uint32_t sum = 0, lo = 0, hi = 0;
 #pragma unroll
                 for (int w = 0; w < kBinWarps; w++) {
-                    const uint32_t v = s_cnt[w * kBandTilesMax + k];
+                    const uint32_t v = s_cnt[w * band_max + k];
                     if (w < 4) lo |= v << (8 * w); else hi |= v << (8 * (w - 4));
                     sum += v;
                 }
@@ -1051,10 +1108,11 @@ __global__ void __launch_bounds__(32 * kBinWarps) tile_bins_kernel(TileBinArgs a
             }
         } else if (kStaged) {
             // copy the band out: slot i of the local buffer goes to s_base[tile] + i
-            const uint32_t staged = min(n_local, (uint32_t)kStageCap);
+            const uint32_t staged = min(n_local, (uint32_t)kCap);
             for (uint32_t i = threadIdx.x; i < staged; i += 32 * kBinWarps) {
-                const uint32_t pos = s_base[s_otile[i]] + i;
-                if (pos < a.cap) a.point_list[pos] = s_oid[i];
+                const uint32_t v = s_oid[i];
+                const uint32_t pos = s_base[v & 0xffffu] + i;
+                if (pos < a.cap) a.point_list[pos] = s_id[v >> 16];
             }
         }
         __syncthreads();  // counters and staging free for the next band
@@ -1151,7 +1209,9 @@ static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t s
     // stage the output through shared memory when a (batch, tile) cell holds enough instances to coalesce
     static const int forced_staged = [] { const char* e = getenv("B3GS_BIN_STAGED"); return e ? atoi(e) : -1; }();
     const bool staged = forced_staged >= 0 ? forced_staged != 0 : (double)a.R >= 3.5 * (double)L.nb * (double)L.T;
-    const size_t smem_count = bin_smem_bytes(L.B, false, false), smem_scatter = bin_smem_bytes(L.B, true, staged);
+    const int band_max = std::max(bin_band_max(), (a.grid_x + 1) & ~1), stage_cap = bin_stage_cap(L.B, band_max);
+    const size_t smem_count = bin_smem_bytes(L.B, band_max, false, 0),
+                 smem_scatter = bin_smem_bytes(L.B, band_max, true, staged ? stage_cap : 0);
     static thread_local int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1163,7 +1223,7 @@ static cudaError_t tile_bins(const BinningPhase2Args& a, char* q, cudaStream_t s
     }
     TileBinArgs k;
     k.P = a.P; k.B = L.B; k.nb = L.nb; k.T = L.T; k.T_pad = L.T_pad; k.grid_x = a.grid_x; k.grid_y = a.grid_y;
-    k.band_rows = L.band_rows;
+    k.band_rows = L.band_rows; k.band_max = band_max; k.stage_cap = stage_cap;
     k.cap = (uint32_t)a.R;
     k.sorted_ids = a.sorted_ids; k.rects = a.rects; k.table = table; k.point_list = a.point_list;
     k.wcount = reinterpret_cast<uint2*>(q + L.wcount);
