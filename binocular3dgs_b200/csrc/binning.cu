@@ -1139,17 +1139,27 @@ __global__ void __launch_bounds__(256) bin_chunk_sums(const uint32_t* __restrict
 __global__ void __launch_bounds__(1024) bin_tile_scan(uint32_t* __restrict__ tile_total, int T, uint2* __restrict__ ranges,
                                                      uint32_t cap) {
     __shared__ uint32_t s_warp[32];
+    constexpr int kPer = 8;   // consecutive tiles per thread: one block scan per 8192 tiles (dtu: 7500)
     uint32_t carry = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + threadIdx.x;
-        const uint32_t v = t < T ? tile_total[t] : 0u;
+    for (int base = 0; base < T; base += 1024 * kPer) {
+        const int t0 = base + threadIdx.x * kPer;
+        uint32_t v[kPer], sum = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            v[j] = t0 + j < T ? tile_total[t0 + j] : 0u;
+            sum += v[j];
+        }
         uint32_t total;
-        const uint32_t inc = block_inclusive_scan(v, s_warp, total);
-        if (t < T) {
-            const uint32_t start = carry + inc - v;
-            tile_total[t] = start;
-            // cap: only the no-sync forward can see more instances than the list holds; it drops them
-            ranges[t] = v ? make_uint2(min(start, cap), min(start + v, cap)) : make_uint2(0u, 0u);
+        const uint32_t inc = block_inclusive_scan(sum, s_warp, total);
+        uint32_t start = carry + inc - sum;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (t0 + j < T) {
+                tile_total[t0 + j] = start;
+                // cap: only the no-sync forward can see more instances than the list holds; it drops them
+                ranges[t0 + j] = v[j] ? make_uint2(min(start, cap), min(start + v[j], cap)) : make_uint2(0u, 0u);
+            }
+            start += v[j];
         }
         carry += total;
     }
