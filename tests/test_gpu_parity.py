@@ -584,6 +584,26 @@ def test_binning_with_screen_filling_gaussians(nat, ref, dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("W,H", [(20000, 48), (48, 20000), (32640, 16), (1250 * 16, 400)])
+def test_binning_on_extreme_tile_grids(W, H, nat, ref, dev):
+    """Tile rows wider than the default band of the direct tile binning (one row per band, up to the
+    2040-tile limit of the packed widths), 1250 rows of 3 tiles (bands capped at 200 rows), and a
+    grid whose bands hold several wide rows: lists, ranges and images stay those of the reference."""
+    P = 6000
+    scene = make_scene(P, seed=67, scale_lo=0.02, scale_hi=0.3).to(dev)
+    cam = make_camera(W, H, azimuth=0.3).to(dev)
+    bg = torch.tensor([0.2, 0.1, 0.4], device=dev)
+    fn, fr = util.raw_forward(nat, scene, cam, bg), util.raw_forward(ref, scene, cam, bg)
+    inn, inr = util.internals(nat, fn, P, W, H), util.internals(ref, fr, P, W, H)
+    assert fn["R"] == fr["R"] and fn["R"] > 0
+    assert (inn["point_list"] == inr["point_list"]).all()
+    assert (inn["ranges"] == inr["ranges"]).all()
+    assert (inn["n_contrib"] == inr["n_contrib"]).all()
+    for k in ("color", "depth", "alpha"):
+        assert (_bits(fn[k]) == _bits(fr[k])).all(), k
+
+
+@pytest.mark.gpu
 def test_forward_and_backward_capture_into_a_cuda_graph(nat, dev):
     """With the no-sync forward nothing on the path blocks the host, so forward + backward can be
     captured into ONE CUDA graph (12 kernel nodes, the cooperative depth sort included) and replayed
