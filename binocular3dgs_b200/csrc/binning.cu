@@ -12,14 +12,14 @@
 //
 //   phase 1 (P-sized, runs while the host waits for R):
 //     stable LSD sort of the P Gaussians by float_bits(depth)        4 x 8-bit passes
-//     exclusive scan of tiles_touched in that order                   -> emission offsets
+//     (fallback path only) exclusive scan of tiles_touched in that order -> emission offsets
 //   phase 2 (R-sized), default — direct tile binning, ONE pass over the instances:
 //     count   per (batch of depth-consecutive Gaussians, tile) instance counts     table[nb][T]
 //     scan    along the batches per tile, then over the tiles                      -> ranges
-//     scatter every batch walks its Gaussians in depth order with the tile counters in
-//             shared memory (loaded by one TMA bulk copy) and stores each id at its final
-//             position: 4 B written per instance, nothing else R-sized is touched
-//   phase 2, fallback (tile grid wider than kBandTilesMax; B3GS_BINNING=radix):
+//     scatter every batch walks its Gaussians in depth order, band of tile rows by band, with the
+//             band's counters in shared memory; the ids are staged in a block-local tile-major
+//             buffer and copied out coalesced: 4 B written per instance, nothing else R-sized
+//   phase 2, fallback (tile rows wider than kBandTilesMax; B3GS_BINNING=radix):
 //     emit (tile, id) instances in depth order, one warp per 32 Gaussians
 //     stable LSD sort of the instances by tile id                     ceil(bits(T)/8) passes
 //     tile ranges from the sorted tile ids
@@ -824,7 +824,7 @@ static int tile_passes(int T) {
 // all measured on B200 at 1M Gaussians / 1600x1200 / 42M instances (profiles/README.md r02c-d):
 //  (i)  one warp walking 512 Gaussians against all T counters is a 28 000-instruction dependent
 //       chain at 7 warps per SM — 230 us for the count alone; eight short chains per block
-//       and four blocks per SM hide most of that latency (156 us);
+//       and several blocks per SM hide most of that latency (156 us, 103 us in the final form);
 //  (ii) written in depth order, every 32-byte sector of the output stays half-written for the
 //       lifetime of a batch, the open sectors of ~1000 concurrent batches (85 MB) do not fit
 //       the L2 and each is evicted and re-fetched (1.8 GB of DRAM traffic for a 169 MB list,
@@ -832,10 +832,11 @@ static int tile_passes(int T) {
 //       time and most sectors complete while resident (0.38 GB, 0.46 ms);
 //  (iii) an instance-parallel variant (lane = Gaussian, per-tile chunk masks for the rank)
 //       loses to lane divergence over the rectangle sizes: 1.37 ms.
-// What remains is the dependent walk and the 4-byte scattered store itself (~110 G stores/s):
-// depth sort + binning 0.677 ms against 0.777 ms for emit + two radix passes at 42 instances
-// per Gaussian (1M / 1600x1200), 0.126 against 0.141 ms at 16 (200k / 800x800).  Bit-identical
-// output either way: a stable distribution by tile of a (depth, id)-ordered sequence.
+// With direct 4-byte stores from the walk (~110 G stores/s) depth sort + binning took 0.677 ms
+// against 0.777 ms for emit + two radix passes at 42 instances per Gaussian (1M / 1600x1200),
+// 0.126 against 0.141 ms at 16 (200k / 800x800); staging the band in shared memory and copying it
+// out coalesced (tile_bins_kernel below) brought the 1M case to 0.44 ms.  Bit-identical output
+// either way: a stable distribution by tile of a (depth, id)-ordered sequence.
 constexpr int kBinChunk = 32;            // batches per scan chunk
 constexpr int kBinWarps = 8;             // warps per block = sub-batches per batch
 constexpr int kBandTilesMax = 2040;      // widest tile row / largest band the direct path takes (a width is packed in 11 bits)
