@@ -150,6 +150,7 @@ struct PreBackwardArgs {
     float* dL_dscale;    // [P,3]
     float* dL_drot;      // [P,4]
     int accumulate;      // != 0: dL_dmean3D, dL_dsh, dL_dopacity, dL_dscale, dL_drot are added to, not overwritten
+    int stage;           // set by the launcher: strided outputs staged through shared memory
 };
 void launch_preprocess_backward(const PreBackwardArgs& a, cudaStream_t stream, int first = 0, int count = -1);
 

@@ -57,8 +57,21 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float s
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kernel(PreBackwardArgs p) {
     const int idx = p.first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.first + p.count) return;
+    // Optional (p.stage, B3GS_PREBWD_STAGE=1; OFF by default): outputs with a 12-byte (or 12 M-byte) stride per
+    // Gaussian — dL_dsh, dL_dmean3D, dL_dscale, dL_dmean2D — staged per block in shared memory
+    // ([component][thread], padded) and written out with consecutive threads on consecutive floats, so that a
+    // warp store covers 4 full sectors instead of 12-32 partial ones (ncu r02t: 15.7 sectors per store request).
+    // Measured on B200: it LOSES — 1M Gaussians 82.4 vs 75.3 us, 200k 25.1 vs 25.0, 300k 32.0 vs 31.3 — the L2
+    // already merges the partial sectors (DRAM writes = the algorithmic bytes either way) and the barrier plus
+    // the extra shared-memory round trip cost more than the shorter store queue saves.
+    extern __shared__ float s_out[];
+    const bool staged = p.stage != 0;
+    constexpr int kPitch = kThreads + 1;
+    const int c_mean3d = 3 * p.M, c_scale = c_mean3d + 3, c_mean2d = c_scale + 3;
+    const bool live = idx < p.first + p.count;
+    if (!live && !staged) return;
     const size_t i = (size_t)idx;
+    if (live) {
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -212,7 +225,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kern
     {                                                            \
         const float cf_ = (coef);                                \
         float* d_ = ((k) == 0 ? dsh0 : dshk) + 3 * (k);          \
-        if (acc) {                                               \
+        if (staged) {                                            \
+            s_out[(3 * (k) + 0) * kPitch + threadIdx.x] = cf_ * dRGB[0]; \
+            s_out[(3 * (k) + 1) * kPitch + threadIdx.x] = cf_ * dRGB[1]; \
+            s_out[(3 * (k) + 2) * kPitch + threadIdx.x] = cf_ * dRGB[2]; \
+        } else if (acc) {                                        \
             d_[0] += cf_ * dRGB[0];                              \
             d_[1] += cf_ * dRGB[1];                              \
             d_[2] += cf_ * dRGB[2];                              \
@@ -281,8 +298,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kern
             }
 #undef SHV
 #undef DSH
-            for (int k = ncoef; k < p.M && !acc; k++) {
-                dshk[3 * k] = 0.f; dshk[3 * k + 1] = 0.f; dshk[3 * k + 2] = 0.f;
+            if (staged) {
+                for (int c = 3 * ncoef; c < 3 * p.M; c++) s_out[c * kPitch + threadIdx.x] = 0.f;
+            } else {
+                for (int k = ncoef; k < p.M && !acc; k++) {
+                    dshk[3 * k] = 0.f; dshk[3 * k + 1] = 0.f; dshk[3 * k + 2] = 0.f;
+                }
             }
             const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
             const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
@@ -328,15 +349,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kern
             // dL/dscale as written is w.r.t. the UNSCALED parameter only through s; it
             // stores dot(Rt, dMt) without the modifier (backward.cu:322-325) — kept.
         }
+    } else if (dsh0 && staged) {
+        for (int c = 0; c < 3 * p.M; c++) s_out[c * kPitch + threadIdx.x] = 0.f;
     } else if (dsh0 && !acc) {
         dsh0[0] = 0.f; dsh0[1] = 0.f; dsh0[2] = 0.f;
         for (int k = 3; k < p.M * 3; k++) dshk[k] = 0.f;
     }
 
     // ---- write every output element
-    p.dL_dmean2D[3 * i] = g[B3_G_MEAN2D_X];
-    p.dL_dmean2D[3 * i + 1] = g[B3_G_MEAN2D_Y];
-    p.dL_dmean2D[3 * i + 2] = 0.f;
+    if (staged) {
+        s_out[(c_mean2d + 0) * kPitch + threadIdx.x] = g[B3_G_MEAN2D_X];
+        s_out[(c_mean2d + 1) * kPitch + threadIdx.x] = g[B3_G_MEAN2D_Y];
+        s_out[(c_mean2d + 2) * kPitch + threadIdx.x] = 0.f;
+    } else {
+        p.dL_dmean2D[3 * i] = g[B3_G_MEAN2D_X];
+        p.dL_dmean2D[3 * i + 1] = g[B3_G_MEAN2D_Y];
+        p.dL_dmean2D[3 * i + 2] = 0.f;
+    }
     // intermediates a caller may not want (NULL): the reference materialises all of them
     if (p.dL_dconic)
         reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(g[B3_G_CONIC_X], g[B3_G_CONIC_Y], 0.f, g[B3_G_CONIC_W]);
@@ -359,7 +388,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kern
     // The five parameter gradients: overwritten, or — B3GS_BWD_ACCUMULATE, the second view of a
     // step writing into the same exchange bucket — added to what the earlier view left there
     // (dL_dsh was accumulated where it was formed, above).
-    if (acc) {
+    if (staged) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            s_out[(c_mean3d + k) * kPitch + threadIdx.x] = dmean[k];
+            s_out[(c_scale + k) * kPitch + threadIdx.x] = dscale[k];
+        }
+        if (acc) {
+            p.dL_dopacity[idx] += g[B3_G_OPACITY];
+            float4* r4 = reinterpret_cast<float4*>(p.dL_drot) + idx;
+            const float4 o = *r4;
+            *r4 = make_float4(o.x + drot.x, o.y + drot.y, o.z + drot.z, o.w + drot.w);
+        } else {
+            p.dL_dopacity[idx] = g[B3_G_OPACITY];
+            reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
+        }
+    } else if (acc) {
         p.dL_dopacity[idx] += g[B3_G_OPACITY];
         p.dL_dmean3D[3 * i] += dmean[0];
         p.dL_dmean3D[3 * i + 1] += dmean[1];
@@ -380,6 +424,35 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) preprocess_backward_kern
         p.dL_dscale[3 * i + 2] = dscale[2];
         reinterpret_cast<float4*>(p.dL_drot)[idx] = drot;
     }
+    }  // live
+    if (!staged) return;
+    __syncthreads();
+    // copy-out: element e of a region = (Gaussian e / ncomp of the block, component e % ncomp)
+    const int i0 = p.first + blockIdx.x * kThreads;
+    const int nvalid = min(kThreads, p.first + p.count - i0);
+    auto flush = [&](float* dst, int comp0, int ncomp, bool add) {
+        const int total = nvalid * ncomp;
+        int t = (int)threadIdx.x / ncomp, c = (int)threadIdx.x - t * ncomp;
+        const int dt = kThreads / ncomp, dc = kThreads - dt * ncomp;
+        for (int e = threadIdx.x; e < total; e += kThreads) {
+            const float v = s_out[(comp0 + c) * kPitch + t];
+            if (add) dst[e] += v; else dst[e] = v;
+            t += dt; c += dc;
+            if (c >= ncomp) { c -= ncomp; t++; }
+        }
+    };
+    const bool add = p.accumulate != 0;
+    if (p.dL_dsh) {
+        if (p.raw) {
+            flush(p.dL_dsh + (size_t)i0 * 3, 0, 3, add);
+            if (p.M > 1) flush(p.dL_dsh_rest + (size_t)i0 * (p.M - 1) * 3, 3, 3 * (p.M - 1), add);
+        } else {
+            flush(p.dL_dsh + (size_t)i0 * p.M * 3, 0, 3 * p.M, add);
+        }
+    }
+    flush(p.dL_dmean3D + (size_t)i0 * 3, c_mean3d, 3, add);
+    flush(p.dL_dscale + (size_t)i0 * 3, c_scale, 3, add);
+    flush(p.dL_dmean2D + (size_t)i0 * 3, c_mean2d, 3, false);
 }
 
 // Gaussians [first, first + count) (count < 0: all P)
@@ -388,16 +461,26 @@ void launch_preprocess_backward(const PreBackwardArgs& a0, cudaStream_t stream, 
     a.first = first;
     a.count = count < 0 ? a.P - first : count;
     if (a.count <= 0) return;
-    // threads per block x minimum blocks per SM (register cap); B3GS_PREBWD_SHAPE = 0..4 overrides.
+    // threads per block x minimum blocks per SM (register cap); B3GS_PREBWD_SHAPE = 0..5 overrides.
     // Measured on B200, 1M / 200k Gaussians: 256x3 (80 regs, 184 B spilled) 87.0 / 27.2 us, 128x6 80.5 / 25.8,
-    // 128x5 84.5 / 27.1, 128x4 (no spills) 90.8 / 27.1, 64x10 (96 regs, 40 B spilled) 78.7 / 25.2.
-    static const int shape = [] { const char* e = getenv("B3GS_PREBWD_SHAPE"); return e ? atoi(e) : 4; }();
+    // 128x5 84.5 / 27.1, 128x4 (no spills) 90.8 / 27.1, 64x10 (96 regs, 40 B spilled) 78.7 / 25.2; the same shape in
+    // the current form of the kernel (16 B spilled): 75.3 / 25.0 us.  More 64-thread blocks per SM beat fewer spills:
+    // 64x8 (125 regs, none) 88.4 / 27.1, 64x9 76.5 / 25.5, 64x10 75.4 / 25.1, 64x12 (80 regs, 108 B) 72.8 / 24.8 =
+    // 3.39 TB/s, 52 % of the measured HBM peak (default), 64x14 (72 regs, 208 B) 73.0 / 25.6, 64x16 (64 regs) 81.0 / 30.3.
+    static const int shape = [] { const char* e = getenv("B3GS_PREBWD_SHAPE"); return e ? atoi(e) : 5; }();
+    // staged outputs (B3GS_PREBWD_STAGE=1; measured slower, see the kernel): (3 M + 9) columns of threads + 1 floats
+    static const int stage = [] { const char* e = getenv("B3GS_PREBWD_STAGE"); return e ? atoi(e) : 0; }();
+    const int threads = shape >= 4 && shape <= 5 ? 64 : (shape >= 1 && shape <= 3 ? 128 : 256);
+    size_t smem = (size_t)(3 * a.M + 9) * (threads + 1) * sizeof(float);
+    a.stage = stage && smem <= 48 * 1024;
+    if (!a.stage) smem = 0;
     switch (shape) {
-        case 1: preprocess_backward_kernel<128, 6><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 85 regs
-        case 2: preprocess_backward_kernel<128, 5><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 102 regs
-        case 3: preprocess_backward_kernel<128, 4><<<(a.count + 127) / 128, 128, 0, stream>>>(a); break;   // 128 regs
-        case 4: preprocess_backward_kernel<64, 10><<<(a.count + 63) / 64, 64, 0, stream>>>(a); break;      // 102 regs
-        default: preprocess_backward_kernel<256, 3><<<(a.count + 255) / 256, 256, 0, stream>>>(a); break;  // 80 regs
+        case 1: preprocess_backward_kernel<128, 6><<<(a.count + 127) / 128, 128, smem, stream>>>(a); break;   // 85 regs
+        case 2: preprocess_backward_kernel<128, 5><<<(a.count + 127) / 128, 128, smem, stream>>>(a); break;   // 102 regs
+        case 3: preprocess_backward_kernel<128, 4><<<(a.count + 127) / 128, 128, smem, stream>>>(a); break;   // 128 regs
+        case 4: preprocess_backward_kernel<64, 10><<<(a.count + 63) / 64, 64, smem, stream>>>(a); break;      // 96 regs
+        case 5: preprocess_backward_kernel<64, 12><<<(a.count + 63) / 64, 64, smem, stream>>>(a); break;      // 80 regs
+        default: preprocess_backward_kernel<256, 3><<<(a.count + 255) / 256, 256, smem, stream>>>(a); break;  // 80 regs
     }
     count_launch();
 }
